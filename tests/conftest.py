@@ -1,0 +1,20 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: long-running CPU check")
+
+
+@pytest.fixture(scope="session")
+def zk():
+    """The initialised C-ABI library; GPU tests fail (not skip) if it cannot start."""
+    from zukelang_b200 import _lib
+    return _lib.lib()

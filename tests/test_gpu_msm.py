@@ -1,0 +1,115 @@
+"""G1 / G2 MSM through the C ABI against the oracle's restatement of the
+reference folds (curve.ml:91-118).  Bit-exact on uncompressed + compressed bytes."""
+import ctypes
+import random
+
+import pytest
+
+from oracle import bls12_381 as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+R = O.R
+
+GROUPS = {
+    "G1": (O.G1, H.g1_bytes, H.expect_g1, 144, "zk_g1_msm", "zk_g1_table_load", "zk_g1_table_msm", "zk_g1_fixed_base_mul", 96),
+    "G2": (O.G2, H.g2_bytes, H.expect_g2, 288, "zk_g2_msm", "zk_g2_table_load", "zk_g2_table_msm", "zk_g2_fixed_base_mul", 192),
+}
+
+
+def _msm(zk, gname, pts, ks, inf_flags=None):
+    from zukelang_b200 import _lib
+    G, enc, _, outn, fn = GROUPS[gname][:5]
+    out = H.out_buf(outn)
+    flags = bytes(inf_flags) if inf_flags is not None else None
+    _lib.check(getattr(zk, fn)(enc(pts), flags, H.scalars_bytes(ks), len(pts), out))
+    return bytes(out)
+
+
+@pytest.mark.parametrize("gname", ["G1", "G2"])
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 255, 256])
+def test_msm_random(zk, gname, n):
+    G, _, expect = GROUPS[gname][:3]
+    rng = random.Random(n * 31 + len(gname))
+    if gname == "G2" and n > 64:
+        n = 64 + (n % 7)
+    pts, _ = H.random_points(G, n, rng)
+    ks = [rng.randrange(R) for _ in range(n)]
+    assert _msm(zk, gname, pts, ks) == expect(H.oracle_msm(G, pts, ks))
+
+
+@pytest.mark.parametrize("gname", ["G1", "G2"])
+def test_msm_edge_scalars_and_bases(zk, gname):
+    """Edge scalars {0, 1, r-1, 2^k} and edge bases {O, P and -P, repeated P}."""
+    G, _, expect = GROUPS[gname][:3]
+    rng = random.Random(99)
+    p = G.mul(G.one, 7)
+    q = G.mul(G.one, 11)
+    pts = [p, G.neg(p), p, p, None, q, q, G.one, q, p]
+    ks = [5, 5, 0, 1, 1234, R - 1, 1 << 254 if (1 << 254) < R else 1 << 200, 1 << 64, 1 << 15, (1 << 16) - 1]
+    ks = [k % R for k in ks]
+    assert _msm(zk, gname, pts, ks) == expect(H.oracle_msm(G, pts, ks))
+    # sum cancels to the identity
+    assert _msm(zk, gname, [p, G.neg(p)], [9, 9]) == expect(None)
+    # all scalars zero
+    assert _msm(zk, gname, [p, q], [0, 0]) == expect(None)
+    # identity given through inf_flags rather than the 0x40 encoding
+    assert _msm(zk, gname, [p, q], [3, 4], inf_flags=[0, 1]) == expect(G.mul(p, 3))
+    # repeated point with many equal scalars hits the P + P (doubling) branch of the mixed add
+    assert _msm(zk, gname, [p] * 8, [1] * 8) == expect(G.mul(p, 8))
+
+
+def test_msm_empty_is_identity(zk):
+    from zukelang_b200 import _lib
+    out = H.out_buf(144)
+    _lib.check(zk.zk_g1_msm(None, None, None, 0, out))
+    assert bytes(out) == H.expect_g1(None)
+
+
+def test_msm_rejects_bad_inputs(zk):
+    from zukelang_b200 import _lib
+    out = H.out_buf(144)
+    bad_point = bytes(95) + b"\x01"                       # (0, 1) is not on the curve
+    assert zk.zk_g1_msm(bad_point, None, O.fr_to_bytes(1), 1, out) == _lib.ZK_EPOINT
+    good = O.g1_to_uncompressed(O.G1.one)
+    assert zk.zk_g1_msm(good, None, (R).to_bytes(32, "little"), 1, out) == _lib.ZK_EPOINT  # scalar == r
+    with pytest.raises(_lib.InvalidArgument):
+        _lib.check(zk.zk_g1_msm(good, None, None, 1, out))
+
+
+@pytest.mark.parametrize("gname,n", [("G1", 1000), ("G1", 4096), ("G2", 300)])
+@pytest.mark.parametrize("precompute", [0, 1])
+def test_table_msm_known_dlog(zk, gname, n, precompute):
+    """Resident table (with and without the precomputed windows): bases k_i * G from the
+    fixed-base kernel, result checked against (sum s_i k_i) * G — exact at any size."""
+    from zukelang_b200 import _lib
+    G, enc, expect, outn, _, load, msm, fixed, raw = GROUPS[gname]
+    rng = random.Random(n + precompute)
+    dl = [rng.randrange(R) for _ in range(n)]
+    dl[3] = 0                                              # an identity base inside the table
+    bases = (ctypes.c_uint8 * (raw * n))()
+    _lib.check(getattr(zk, fixed)(H.scalars_bytes(dl), n, bases))
+    # spot-check the fixed-base kernel itself against the oracle
+    for i in (0, 3, n - 1):
+        pt = G.mul(G.one, dl[i])
+        exp = O.g1_to_uncompressed(pt) if gname == "G1" else O.g2_to_uncompressed(pt)
+        assert bytes(bases[i * raw:(i + 1) * raw]) == exp
+    h = ctypes.c_uint64()
+    _lib.check(getattr(zk, load)(bases, None, n, precompute, 0, ctypes.byref(h)))
+    try:
+        for trial in range(2):
+            ks = [rng.randrange(R) for _ in range(n)]
+            if trial == 1:                                 # witness-like: mostly 0 / 1
+                ks = [k if rng.random() < 0.1 else rng.randrange(2) for k in ks]
+            out = H.out_buf(outn)
+            _lib.check(getattr(zk, msm)(h.value, H.scalars_bytes(ks), n, out))
+            total = sum(s * d for s, d in zip(ks, dl)) % R
+            assert bytes(out) == expect(G.mul(G.one, total))
+        # prefix MSM (fewer scalars than table points)
+        m = n // 3
+        ks = [rng.randrange(R) for _ in range(m)]
+        out = H.out_buf(outn)
+        _lib.check(getattr(zk, msm)(h.value, H.scalars_bytes(ks), m, out))
+        assert bytes(out) == expect(G.mul(G.one, sum(s * d for s, d in zip(ks, dl)) % R))
+    finally:
+        _lib.check(zk.zk_table_free(h.value))

@@ -1,0 +1,103 @@
+"""ctypes binding of libzkb200.so — the same symbols the OCaml foreign_stubs bind
+(INTEGRATION.md).  Fails loudly when the library is missing: there is no
+fallback implementation."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+
+ZK_OK, ZK_EARG, ZK_EPOINT, ZK_ECUDA, ZK_EREMAINDER = 0, -1, -2, -3, -4
+FR_BYTES, G1_RAW, G1_COMP, G1_OUT, G2_RAW, G2_COMP, G2_OUT = 32, 96, 48, 144, 192, 96, 288
+
+
+class ZkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("libzkb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class InvalidArgument(ZkError, ValueError):
+    """OCaml's Invalid_argument (ZK_EARG)."""
+
+
+_u8p = POINTER(c_uint8)
+_u32p = POINTER(c_uint32)
+
+# name -> (restype, argtypes); mirrors include/zkb200.h one to one
+SIGNATURES = {
+    "zk_init": (c_int, [c_int]),
+    "zk_shutdown": (c_int, []),
+    "zk_last_error": (c_char_p, []),
+    "zk_device_info": (c_int, [c_char_p, c_size_t]),
+    "zk_g1_msm": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "zk_g2_msm": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "zk_g1_table_load": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, POINTER(c_uint64)]),
+    "zk_g2_table_load": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, POINTER(c_uint64)]),
+    "zk_g1_table_msm": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p]),
+    "zk_g2_table_msm": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p]),
+    "zk_g1_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "zk_g2_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "zk_table_info": (c_int, [c_uint64, POINTER(c_uint64)]),
+    "zk_table_free": (c_int, [c_uint64]),
+    "zk_g1_fixed_base_mul": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "zk_g2_fixed_base_mul": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "zk_bench_intpipe": (c_int, [c_int, c_int, POINTER(c_double), POINTER(c_double)]),
+    "zk_test_field_op": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
+}
+
+_lib = None
+_initialised = False
+
+
+def load(path: str | None = None) -> ctypes.CDLL:
+    """dlopen libzkb200.so and declare every prototype.  No device needed."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(
+            "libzkb200.so not found at %s — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C zukelang_b200/csrc`; there is no CPU fallback" % p)
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        if not hasattr(lib, name):
+            continue                      # reported by tests/test_abi.py
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc == ZK_OK:
+        return
+    msg = (load().zk_last_error() or b"").decode("utf-8", "replace")
+    if rc == ZK_EARG:
+        raise InvalidArgument(rc, msg)
+    raise ZkError(rc, msg)
+
+
+def lib() -> ctypes.CDLL:
+    """The initialised library (selects the device of LOCAL_RANK, else device 0)."""
+    global _initialised
+    l = load()
+    if not _initialised:
+        dev = int(os.environ.get("ZKB200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        check(l.zk_init(dev))
+        _initialised = True
+    return l
+
+
+def buf(data) -> ctypes.Array:
+    """bytes-like -> ctypes array usable as a void* argument (zero copy for bytearray)."""
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        b = bytes(data) if not isinstance(data, bytes) else data
+        return ctypes.create_string_buffer(b, len(b))
+    return data

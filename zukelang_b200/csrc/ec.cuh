@@ -1,0 +1,187 @@
+// Fp2 tower and short-Weierstrass (a = 0) point arithmetic in XYZZ coordinates,
+// generic over the base field so G1 (Fp) and G2 (Fp2) share one implementation.
+//
+// Replaces Bls12_381.G1/G2.{add, mul, negate} as wrapped by ExtendG at
+// /root/reference/src/lib/zk/curve.ml:159-191.
+//
+// XYZZ: x = X/ZZ, y = Y/ZZZ with ZZ^3 = ZZZ^2; the identity is ZZ = 0.
+// Mixed addition (affine addend) costs 8M + 2S, general addition 12M + 2S,
+// doubling 6M + 4S-ish (EFD: madd-2008-s, add-2008-s, dbl-2008-s-1, mdbl-2008-s-1).
+#pragma once
+#include "mont.cuh"
+#include "params.cuh"
+
+typedef Mont<FpParams> Fp;
+typedef Mont<FrParams> Fr;
+
+// -------------------------------------------------------------------------
+// Fp2 = Fp[u] / (u^2 + 1)
+// -------------------------------------------------------------------------
+struct Fp2 {
+  Fp c0, c1;
+  static ZK_HD Fp2 zero() { return Fp2{Fp::zero(), Fp::zero()}; }
+  static ZK_HD Fp2 one() { return Fp2{Fp::one(), Fp::zero()}; }
+  ZK_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  ZK_HD bool operator==(const Fp2& b) const { return c0 == b.c0 && c1 == b.c1; }
+  ZK_HD bool operator!=(const Fp2& b) const { return !(*this == b); }
+  friend ZK_HD Fp2 operator+(const Fp2& a, const Fp2& b) { return Fp2{a.c0 + b.c0, a.c1 + b.c1}; }
+  friend ZK_HD Fp2 operator-(const Fp2& a, const Fp2& b) { return Fp2{a.c0 - b.c0, a.c1 - b.c1}; }
+  ZK_HD Fp2 neg() const { return Fp2{c0.neg(), c1.neg()}; }
+  ZK_HD Fp2 dbl() const { return Fp2{c0.dbl(), c1.dbl()}; }
+  // Karatsuba: 3 Fp products
+  friend ZK_HD Fp2 operator*(const Fp2& a, const Fp2& b) {
+    Fp t0 = Fp::mul_call(a.c0, b.c0);
+    Fp t1 = Fp::mul_call(a.c1, b.c1);
+    Fp t2 = Fp::mul_call(a.c0 + a.c1, b.c0 + b.c1);
+    return Fp2{t0 - t1, t2 - t0 - t1};
+  }
+  // (c0 + c1 u)^2 = (c0 + c1)(c0 - c1) + 2 c0 c1 u : 2 Fp products
+  ZK_HD Fp2 sqr() const {
+    Fp s = c0 + c1;
+    Fp d = c0 - c1;
+    Fp m = Fp::mul_call(c0, c1);
+    return Fp2{Fp::mul_call(s, d), m.dbl()};
+  }
+  ZK_NI Fp2 inverse() const {
+    Fp n = Fp::mul_call(c0, c0) + Fp::mul_call(c1, c1);
+    Fp ni = n.inverse();
+    return Fp2{Fp::mul_call(c0, ni), Fp::mul_call(c1, ni).neg()};
+  }
+};
+
+// -------------------------------------------------------------------------
+// points
+// -------------------------------------------------------------------------
+template <class F>
+struct Affine {
+  F x, y;  // identity is encoded as (0, 0), which is not on either curve (b != 0)
+  ZK_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+  static ZK_HD Affine inf() { return Affine{F::zero(), F::zero()}; }
+  ZK_HD Affine neg() const { return Affine{x, y.neg()}; }
+};
+
+template <class F>
+struct XYZZ {
+  F X, Y, ZZ, ZZZ;
+
+  static ZK_HD XYZZ inf() { return XYZZ{F::zero(), F::zero(), F::zero(), F::zero()}; }
+  ZK_HD bool is_inf() const { return ZZ.is_zero(); }
+  static ZK_HD XYZZ from_affine(const Affine<F>& p) {
+    if (p.is_inf()) return inf();
+    return XYZZ{p.x, p.y, F::one(), F::one()};
+  }
+  ZK_HD XYZZ neg() const { return XYZZ{X, Y.neg(), ZZ, ZZZ}; }
+
+  // 2 * (affine p)   — mdbl-2008-s-1
+  static ZK_NI XYZZ dbl_affine(const Affine<F>& p) {
+    if (p.is_inf() || p.y.is_zero()) return inf();
+    F U = p.y.dbl();
+    F V = U.sqr();
+    F W = U * V;
+    F S = p.x * V;
+    F xx = p.x.sqr();
+    F M = xx.dbl() + xx;
+    XYZZ r;
+    r.X = M.sqr() - S.dbl();
+    r.Y = M * (S - r.X) - W * p.y;
+    r.ZZ = V;
+    r.ZZZ = W;
+    return r;
+  }
+
+  // dbl-2008-s-1
+  ZK_NI XYZZ dbl() const {
+    if (is_inf() || Y.is_zero()) return inf();
+    F U = Y.dbl();
+    F V = U.sqr();
+    F W = U * V;
+    F S = X * V;
+    F xx = X.sqr();
+    F M = xx.dbl() + xx;
+    XYZZ r;
+    r.X = M.sqr() - S.dbl();
+    r.Y = M * (S - r.X) - W * Y;
+    r.ZZ = V * ZZ;
+    r.ZZZ = W * ZZZ;
+    return r;
+  }
+
+  // this += affine p   — madd-2008-s, with the exceptional cases handled
+  ZK_HD void madd(const Affine<F>& p) {
+    if (p.is_inf()) return;
+    if (is_inf()) {
+      X = p.x; Y = p.y; ZZ = F::one(); ZZZ = F::one();
+      return;
+    }
+    F U2 = p.x * ZZ;
+    F S2 = p.y * ZZZ;
+    F Pd = U2 - X;
+    F Rd = S2 - Y;
+    if (Pd.is_zero()) {
+      if (Rd.is_zero()) *this = dbl_affine(p);
+      else *this = inf();
+      return;
+    }
+    F PP = Pd.sqr();
+    F PPP = Pd * PP;
+    F Q = X * PP;
+    F X3 = Rd.sqr() - PPP - Q.dbl();
+    Y = Rd * (Q - X3) - Y * PPP;
+    X = X3;
+    ZZ = ZZ * PP;
+    ZZZ = ZZZ * PPP;
+  }
+
+  // this += q   — add-2008-s
+  ZK_NI void add(const XYZZ& q) {
+    if (q.is_inf()) return;
+    if (is_inf()) { *this = q; return; }
+    F U1 = X * q.ZZ;
+    F U2 = q.X * ZZ;
+    F S1 = Y * q.ZZZ;
+    F S2 = q.Y * ZZZ;
+    F Pd = U2 - U1;
+    F Rd = S2 - S1;
+    if (Pd.is_zero()) {
+      if (Rd.is_zero()) *this = dbl();
+      else *this = inf();
+      return;
+    }
+    F PP = Pd.sqr();
+    F PPP = Pd * PP;
+    F Q = U1 * PP;
+    F X3 = Rd.sqr() - PPP - Q.dbl();
+    Y = Rd * (Q - X3) - S1 * PPP;
+    X = X3;
+    ZZ = ZZ * q.ZZ * PP;
+    ZZZ = ZZZ * q.ZZZ * PPP;
+  }
+
+  // affine coordinates (one field inversion); identity -> (0, 0)
+  ZK_NI Affine<F> to_affine() const {
+    if (is_inf()) return Affine<F>::inf();
+    // 1/ZZZ * ZZ = 1/Z  ->  1/ZZ = (1/Z)^2
+    F izzz = ZZZ.inverse();
+    F iz = izzz * ZZ;
+    F izz = iz.sqr();
+    return Affine<F>{X * izz, Y * izzz};
+  }
+};
+
+// k * p for a canonical little-endian 8-limb scalar (double-and-add, MSB first)
+template <class F>
+ZK_NI XYZZ<F> scalar_mul(const XYZZ<F>& p, const uint32_t* k, int nlimbs = 8) {
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int i = nlimbs - 1; i >= 0; i--) {
+    for (int bit = 31; bit >= 0; bit--) {
+      acc = acc.dbl();
+      if ((k[i] >> bit) & 1) acc.add(p);
+    }
+  }
+  return acc;
+}
+
+typedef Affine<Fp> G1Affine;
+typedef Affine<Fp2> G2Affine;
+typedef XYZZ<Fp> G1XYZZ;
+typedef XYZZ<Fp2> G2XYZZ;

@@ -1,0 +1,209 @@
+// Montgomery prime-field arithmetic on 32-bit limbs, carries held in registers.
+//
+// One template serves Fp (N = 12, 381-bit) and Fr (N = 8, 255-bit).  The
+// parameter class P supplies N and constexpr limb accessors (mod, r2, one, n0)
+// so that after full unrolling every modulus limb is an immediate operand of
+// its IMAD.
+//
+// Replaces the Fp/Fr arithmetic the reference reaches through the bls12-381
+// package (call sites /root/reference/src/lib/zk/curve.ml:121-171).
+//
+// Multiplication is CIOS Montgomery with the even/odd accumulator split: the
+// 64-bit products a[j]*b_i for even j tile limbs (j, j+1) without overlap, and
+// likewise for odd j one limb higher, so each half is a single uninterrupted
+// mad.lo.cc / madc.hi.cc carry chain (IMAD pipe) with no carry fix-ups between
+// rows.  4N+1 IMADs per row, N rows.
+#pragma once
+#include "ptx.cuh"
+
+template <class P>
+struct alignas(16) Mont {
+  static constexpr int N = P::N;
+  uint32_t v[N];
+
+  // ---- construction -------------------------------------------------------
+  static ZK_HD Mont zero() {
+    Mont r;
+    ZK_UNROLL for (int i = 0; i < N; i++) r.v[i] = 0;
+    return r;
+  }
+  static ZK_HD Mont one() {  // R mod p
+    Mont r;
+    ZK_UNROLL for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+    return r;
+  }
+  static ZK_HD Mont r2() {
+    Mont r;
+    ZK_UNROLL for (int i = 0; i < N; i++) r.v[i] = P::r2(i);
+    return r;
+  }
+
+  ZK_HD bool is_zero() const {
+    uint32_t o = 0;
+    ZK_UNROLL for (int i = 0; i < N; i++) o |= v[i];
+    return o == 0;
+  }
+  ZK_HD bool operator==(const Mont& b) const {
+    uint32_t o = 0;
+    ZK_UNROLL for (int i = 0; i < N; i++) o |= v[i] ^ b.v[i];
+    return o == 0;
+  }
+  ZK_HD bool operator!=(const Mont& b) const { return !(*this == b); }
+
+  // ---- add / sub ----------------------------------------------------------
+  // r = (a >= p) ? a - p : a, for a < 2p given with an extra carry bit `hi`
+  static ZK_HD void final_sub(Mont& a, uint32_t hi) {
+    uint32_t t[N];
+    t[0] = ptx::sub_cc(a.v[0], P::mod(0));
+    ZK_UNROLL for (int i = 1; i < N; i++) t[i] = ptx::subc_cc(a.v[i], P::mod(i));
+    uint32_t borrow = ptx::subc(hi, 0);  // 0 if a - p >= 0, else 0xffffffff
+    ZK_UNROLL for (int i = 0; i < N; i++) a.v[i] = borrow ? a.v[i] : t[i];
+  }
+
+  friend ZK_HD Mont operator+(const Mont& a, const Mont& b) {
+    Mont r;
+    r.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+    ZK_UNROLL for (int i = 1; i < N; i++) r.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    uint32_t hi = ptx::addc(0, 0);
+    final_sub(r, hi);
+    return r;
+  }
+  friend ZK_HD Mont operator-(const Mont& a, const Mont& b) {
+    Mont r;
+    r.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+    ZK_UNROLL for (int i = 1; i < N; i++) r.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = ptx::subc(0, 0);  // 0 or 0xffffffff
+    uint32_t t[N];
+    t[0] = ptx::add_cc(r.v[0], P::mod(0) & borrow);
+    ZK_UNROLL for (int i = 1; i < N; i++) t[i] = ptx::addc_cc(r.v[i], P::mod(i) & borrow);
+    ZK_UNROLL for (int i = 0; i < N; i++) r.v[i] = t[i];
+    return r;
+  }
+  ZK_HD Mont neg() const {
+    Mont r;
+    if (is_zero()) return *this;
+    r.v[0] = ptx::sub_cc(P::mod(0), v[0]);
+    ZK_UNROLL for (int i = 1; i < N; i++) r.v[i] = ptx::subc_cc(P::mod(i), v[i]);
+    return r;
+  }
+  ZK_HD Mont dbl() const { return *this + *this; }
+
+  // ---- Montgomery product ---------------------------------------------------
+  // acc[j], acc[j+1] = lo, hi of a[j] * bi for j = 0, 2, .. n-2
+  template <int n>
+  static ZK_HD void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+    ZK_UNROLL for (int j = 0; j < n; j += 2) {
+      acc[j] = ptx::mul_lo(a[j], bi);
+      acc[j + 1] = ptx::mul_hi(a[j], bi);
+    }
+  }
+  // acc[0..n) += (a[0], a[2], ..) * bi as one carry chain; carry-out left in CC
+  template <int n>
+  static ZK_HD void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+    acc[0] = ptx::mad_lo_cc(a[0], bi, acc[0]);
+    acc[1] = ptx::madc_hi_cc(a[0], bi, acc[1]);
+    ZK_UNROLL for (int j = 2; j < n; j += 2) {
+      acc[j] = ptx::madc_lo_cc(a[j], bi, acc[j]);
+      acc[j + 1] = ptx::madc_hi_cc(a[j], bi, acc[j + 1]);
+    }
+  }
+  // same with the modulus limbs (immediates) starting at limb `off`
+  template <int n, int off>
+  static ZK_HD void cmad_mod(uint32_t* acc, uint32_t mi) {
+    acc[0] = ptx::mad_lo_cc(P::mod(off), mi, acc[0]);
+    acc[1] = ptx::madc_hi_cc(P::mod(off), mi, acc[1]);
+    ZK_UNROLL for (int j = 2; j < n; j += 2) {
+      acc[j] = ptx::madc_lo_cc(P::mod(off + j), mi, acc[j]);
+      acc[j + 1] = ptx::madc_hi_cc(P::mod(off + j), mi, acc[j + 1]);
+    }
+  }
+  // odd[] = (odd[] >> 64) + (a[0], a[2], ..) * bi, consuming the incoming CC
+  static ZK_HD void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi) {
+    ZK_UNROLL for (int j = 0; j < N - 2; j += 2) {
+      odd[j] = ptx::madc_lo_cc(a[j], bi, odd[j + 2]);
+      odd[j + 1] = ptx::madc_hi_cc(a[j], bi, odd[j + 3]);
+    }
+    odd[N - 2] = ptx::madc_lo_cc(a[N - 2], bi, 0);
+    odd[N - 1] = ptx::madc_hi(a[N - 2], bi, 0);
+  }
+  // T += m * p with m chosen so that the low limb cancels
+  static ZK_HD void reduce_row(uint32_t* even, uint32_t* odd) {
+    uint32_t mi = even[0] * P::n0();
+    cmad_mod<N, 1>(odd, mi);
+    cmad_mod<N, 0>(even, mi);
+    odd[N - 1] = ptx::addc(odd[N - 1], 0);
+  }
+  // one CIOS row: (even, odd) <- ((even, odd) >> 32) + a * bi, then reduce.
+  // On entry `odd` is the array that was even-aligned in the previous row.
+  static ZK_HD void mad_row(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
+    even[0] = ptx::add_cc(even[0], odd[1]);
+    madc_n_rshift(odd, a + 1, bi);
+    cmad_n<N>(even, a, bi);
+    odd[N - 1] = ptx::addc(odd[N - 1], 0);
+    reduce_row(even, odd);
+  }
+
+  friend ZK_HD Mont operator*(const Mont& a, const Mont& b) {
+    uint32_t e[N], o[N];
+    mul_n<N>(e, a.v, b.v[0]);
+    mul_n<N>(o, a.v + 1, b.v[0]);
+    reduce_row(e, o);
+    ZK_UNROLL for (int i = 1; i < N; i += 2) {
+      mad_row(o, e, a.v, b.v[i]);
+      if (i + 1 < N) mad_row(e, o, a.v, b.v[i + 1]);
+    }
+    // value = (e >> 32) + o
+    Mont r;
+    r.v[0] = ptx::add_cc(e[0], o[1]);
+    ZK_UNROLL for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(e[i], o[i + 1]);
+    r.v[N - 1] = ptx::addc(e[N - 1], 0);
+    final_sub(r, 0);
+    return r;
+  }
+  ZK_HD Mont sqr() const { return *this * *this; }
+  // out-of-line product for code that is not throughput critical (keeps kernels small)
+  static ZK_NI Mont mul_call(const Mont& a, const Mont& b) { return a * b; }
+
+  // ---- conversions -----------------------------------------------------------
+  ZK_HD Mont to_mont() const { return *this * r2(); }
+  ZK_HD Mont from_mont() const {
+    Mont u = zero();
+    u.v[0] = 1;
+    return *this * u;
+  }
+  // canonical-integer comparison helpers (operate on from_mont'ed values)
+  static ZK_HD bool geq_raw(const uint32_t* a, const uint32_t* b) {  // a >= b
+    ptx::sub_cc(a[0], b[0]);
+    ZK_UNROLL for (int i = 1; i < N; i++) ptx::subc_cc(a[i], b[i]);
+    return ptx::subc(0, 0) == 0;
+  }
+  ZK_HD bool is_canonical_raw() const {  // value < p, for an unreduced limb array
+    uint32_t m[N];
+    ZK_UNROLL for (int i = 0; i < N; i++) m[i] = P::mod(i);
+    return !geq_raw(v, m);
+  }
+
+  // a^e for a little-endian limb exponent (square-and-multiply, MSB first)
+  template <int EN>
+  ZK_NI Mont pow_limbs(const uint32_t (&e)[EN]) const {
+    Mont acc = one();
+    bool started = false;
+    for (int i = EN - 1; i >= 0; i--) {
+      for (int bit = 31; bit >= 0; bit--) {
+        if (started) acc = mul_call(acc, acc);
+        if ((e[i] >> bit) & 1) {
+          acc = started ? mul_call(acc, *this) : *this;
+          started = true;
+        }
+      }
+    }
+    return acc;
+  }
+  // multiplicative inverse by Fermat (a^(p-2)); inverse of 0 is 0
+  ZK_NI Mont inverse() const {
+    uint32_t e[N];
+    e[0] = ptx::sub_cc(P::mod(0), 2);
+    ZK_UNROLL for (int i = 1; i < N; i++) e[i] = ptx::subc_cc(P::mod(i), 0);
+    return pow_limbs<N>(e);
+  }
+};

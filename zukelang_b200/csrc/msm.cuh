@@ -1,0 +1,385 @@
+// Pippenger multi-scalar multiplication for BLS12-381 G1 / G2 on sm_100a.
+//
+// Replaces the reference's "MSM" primitives — the left folds of scalar_mul + add
+// at /root/reference/src/lib/zk/curve.ml:91 (sum_map), :94-103 (dot), :112-118
+// (apply_powers) and the double loop of src/groth16/groth16.ml:116-121
+// (sum_apply_powers) — by one bucket-method MSM per proof element.  The result
+// is the same group element, hence the same serialised bytes.
+//
+// Pipeline (all on the caller's stream, no host round trips):
+//   1. k_digits<COUNT>   signed c-bit digits of every scalar -> bucket histogram
+//   2. k_scan_*          exclusive prefix sum of the histogram
+//   3. k_digits<SCATTER> (bucket, point) pairs placed by counting sort
+//   4. k_accumulate      one thread per (bucket, segment): XYZZ += affine base
+//   5. k_reduce_chunks   running-sum reduction of L buckets per thread
+//      k_reduce_tree     per-window tree sum of the chunk results
+//   6. k_horner          window combine (skipped when the table is precomputed)
+//   7. k_finalize        XYZZ -> affine -> uncompressed + compressed bytes
+//
+// A BaseTable built with `precompute` holds 2^(c*w) * P_i for every window w, so
+// all windows share ONE set of 2^(c-1) buckets: the bucket reduction shrinks W
+// times and the window combine disappears, at the price of W times the table
+// bytes — cheap against 180 GB of HBM3e.
+#pragma once
+#include "common.cuh"
+
+namespace zk {
+
+struct MsmConfig {
+  int c;        // window bits
+  int W;        // number of windows  = ceil(256 / c)
+  int nwb;      // bucket windows: 1 when precomputed, else W
+  uint32_t B;   // buckets per window = 2^(c-1)
+  int S;        // segments per bucket in the accumulation
+  int L;        // buckets per thread in the chunk reduction
+  __host__ __device__ uint32_t nbuckets() const { return (uint32_t)nwb * B; }
+};
+
+int env_int(const char* name, int dflt);
+
+// ------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// c bits of the 256-bit little-endian scalar k starting at bit `pos`
+__device__ __forceinline__ uint32_t scalar_bits(const uint32_t* k, int pos, int c) {
+  int limb = pos >> 5, sh = pos & 31;
+  if (limb >= 8) return 0;
+  uint64_t lo = k[limb];
+  uint64_t hi = (limb + 1 < 8) ? k[limb + 1] : 0;
+  return (uint32_t)(((hi << 32) | lo) >> sh) & ((1u << c) - 1);
+}
+
+// Steps 1 and 3.  Signed-digit recoding: d in [-(2^(c-1) - 1), 2^(c-1)], carry
+// into the next window; zero digits (and identity bases) emit nothing.
+// entry = point index (w * stride + i when precomputed, else i) | sign << 31;
+// n = scalars in this call, stride = points per window of the table.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip, uint32_t n, uint32_t stride,
+         MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (skip && skip[i]) return;
+  uint32_t k[8];
+  const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * (size_t)i);
+  uint4 a = __ldg(sp), b = __ldg(sp + 1);
+  k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+  if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) return;
+  uint32_t carry = 0;
+  const uint32_t half = cfg.B;  // 2^(c-1)
+  for (int w = 0; w < cfg.W; w++) {
+    uint32_t d = scalar_bits(k, w * cfg.c, cfg.c) + carry;
+    uint32_t neg = 0;
+    if (d > half) { d = (1u << cfg.c) - d; neg = 1; carry = 1; } else carry = 0;
+    if (d == 0) continue;
+    uint32_t bucket = (cfg.nwb == 1 ? 0u : (uint32_t)w * cfg.B) + d - 1;
+    if (SCATTER) {
+      uint32_t pos = atomicAdd(&counts_or_cursor[bucket], 1u);
+      uint32_t idx = (cfg.nwb == 1) ? (uint32_t)w * stride + i : i;
+      entries[pos] = idx | (neg << 31);
+    } else {
+      atomicAdd(&counts_or_cursor[bucket], 1u);
+    }
+  }
+}
+
+// Step 2: three-kernel exclusive scan (2048 elements per block).
+constexpr int SCAN_THREADS = 512, SCAN_ITEMS = 4, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t ws = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+    uint32_t winc = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    warp_sums[lane] = winc - ws;  // exclusive
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  return warp_sums[wid] + inc - v;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t total;
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) if (base + j < n) s += in[base + j];
+  block_exclusive_scan(s, &total, ws);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of tile sums in place (any count, carried tile by tile)
+static __global__ void __launch_bounds__(1024)
+k_scan_spine(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t total;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_sums[i] : 0;
+    uint32_t ex = block_exclusive_scan(v, &total, ws);
+    if (i < ntiles) tile_sums[i] = ex + carry;
+    carry += total;
+    __syncthreads();
+  }
+}
+
+// writes offsets[0..n] (exclusive scan, offsets[n] = grand total) and a copy in cursor[0..n)
+static __global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ tile_sums,
+             uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t ws[32];
+  __shared__ uint32_t total;
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) { v[j] = (base + j < n) ? in[base + j] : 0; s += v[j]; }
+  uint32_t ex = block_exclusive_scan(s, &total, ws) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; j++) {
+    if (base + j < n) { offsets[base + j] = ex; cursor[base + j] = ex; }
+    ex += v[j];
+    if (base + j == n - 1) offsets[n] = ex;
+  }
+}
+
+// Step 4: bucket accumulation.  Thread t owns (bucket b = t % nbuckets, segment s = t / nbuckets)
+// and folds its slice of the sorted entry list into an XYZZ accumulator with mixed adds.
+// Bases are gathered with 128-bit loads; the next base is fetched while the current one is added.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
+             const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ out, uint32_t nbuckets, int S) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbuckets * (uint32_t)S) return;
+  uint32_t b = t % nbuckets, s = t / nbuckets;
+  uint32_t lo = offsets[b], hi = offsets[b + 1];
+  uint32_t len = hi - lo;
+  uint32_t k0 = lo + (uint32_t)(((uint64_t)len * s) / S);
+  uint32_t k1 = lo + (uint32_t)(((uint64_t)len * (s + 1)) / S);
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (k0 < k1) {
+    uint32_t e = entries[k0];
+    Affine<F> cur = load_vec(&bases[e & 0x7fffffffu]);
+    for (uint32_t k = k0; k < k1; k++) {
+      uint32_t e_next = 0;
+      Affine<F> nxt;
+      bool more = k + 1 < k1;
+      if (more) {
+        e_next = entries[k + 1];
+        nxt = load_vec(&bases[e_next & 0x7fffffffu]);
+      }
+      if (e >> 31) cur.y = cur.y.neg();
+      acc.madd(cur);
+      if (more) { cur = nxt; e = e_next; }
+    }
+  }
+  store_vec(&out[t], acc);
+}
+
+// k * p for a small (< 2^31) multiplier
+template <class F>
+__device__ __noinline__ XYZZ<F> small_mul(const XYZZ<F>& p, uint32_t k) {
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (k == 0 || p.is_inf()) return acc;
+  int top = 31 - __clz(k);
+  for (int bit = top; bit >= 0; bit--) {
+    acc = acc.dbl();
+    if ((k >> bit) & 1) acc.add(p);
+  }
+  return acc;
+}
+
+// Step 5a: thread (window wb, chunk ch) reduces L consecutive buckets with the running-sum
+// trick:  V = sum_{j<L} (ch*L + j + 1) * bucket[ch*L + j]  (segments summed on the fly).
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce_chunks(const XYZZ<F>* __restrict__ parts, MsmConfig cfg, XYZZ<F>* __restrict__ chunk_out) {
+  uint32_t chunks_per_window = cfg.B / cfg.L;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= chunks_per_window * (uint32_t)cfg.nwb) return;
+  uint32_t wb = t / chunks_per_window, ch = t % chunks_per_window;
+  uint32_t nb = cfg.nbuckets();
+  uint32_t first = wb * cfg.B + ch * cfg.L;
+  XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+  for (int j = cfg.L - 1; j >= 0; j--) {
+    for (int s = 0; s < cfg.S; s++) {
+      XYZZ<F> p = load_vec_rw(&parts[(size_t)s * nb + first + j]);
+      run.add(p);
+    }
+    acc.add(run);
+  }
+  // acc = sum (j+1) * bucket_j ; run = sum bucket_j ; add (ch*L) * run
+  XYZZ<F> shifted = small_mul(run, ch * (uint32_t)cfg.L);
+  acc.add(shifted);
+  store_vec(&chunk_out[t], acc);
+}
+
+// Step 5b: one block per window sums that window's chunk results (strided serial + smem tree).
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce_tree(const XYZZ<F>* __restrict__ chunk_out, uint32_t chunks_per_window, XYZZ<F>* __restrict__ window_sums) {
+  extern __shared__ uint4 smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  const XYZZ<F>* src = chunk_out + (size_t)blockIdx.x * chunks_per_window;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t i = threadIdx.x; i < chunks_per_window; i += blockDim.x) {
+    XYZZ<F> p = load_vec_rw(&src[i]);
+    acc.add(p);
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
+    if (threadIdx.x < stride) {
+      XYZZ<F> a = sm[threadIdx.x];
+      a.add(sm[threadIdx.x + stride]);
+      sm[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) store_vec(&window_sums[blockIdx.x], sm[0]);
+}
+
+// Step 6: result = sum_w 2^(c*w) * window_sums[w]   (Horner; nwb == 1 just copies)
+template <class F>
+__global__ void k_horner(const XYZZ<F>* __restrict__ window_sums, MsmConfig cfg, XYZZ<F>* __restrict__ result) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  XYZZ<F> acc = load_vec_rw(&window_sums[cfg.nwb - 1]);
+  for (int w = cfg.nwb - 2; w >= 0; w--) {
+    for (int i = 0; i < cfg.c; i++) acc = acc.dbl();
+    XYZZ<F> p = load_vec_rw(&window_sums[w]);
+    acc.add(p);
+  }
+  store_vec(result, acc);
+}
+
+// Step 7: `count` XYZZ results -> RAW + COMP bytes each
+template <class T>
+__global__ void k_finalize(const XYZZ<typename T::F>* __restrict__ results, int count, uint8_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  XYZZ<typename T::F> p = load_vec_rw(&results[i]);
+  Affine<typename T::F> a = p.to_affine();
+  T::serialize(a, out + (size_t)i * (T::RAW + T::COMP));
+}
+
+// ---- table construction ---------------------------------------------------------
+// raw wire bytes -> Montgomery affine, curve check, identity flags
+template <class T>
+__global__ void __launch_bounds__(128)
+k_parse_bases(const uint8_t* __restrict__ raw, const uint8_t* __restrict__ inf_flags, uint32_t n,
+              Affine<typename T::F>* __restrict__ out, uint8_t* __restrict__ skip, int* __restrict__ err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<typename T::F> p;
+  int bad = 0;
+  if (inf_flags && inf_flags[i]) p = Affine<typename T::F>::inf();
+  else bad = T::parse(raw + (size_t)i * T::RAW, p);
+  if (bad) { atomicExch(err, 1); p = Affine<typename T::F>::inf(); }
+  store_vec(&out[i], p);
+  skip[i] = p.is_inf() ? 1 : 0;
+}
+
+template <class F>
+__global__ void k_mark_skip(const Affine<F>* __restrict__ pts, uint32_t n, uint8_t* __restrict__ skip) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = load_vec_rw(&pts[i]);
+  skip[i] = p.is_inf() ? 1 : 0;
+}
+
+// window w of the precomputed table from window w-1:  P -> 2^c * P   (XYZZ scratch)
+template <class F>
+__global__ void __launch_bounds__(128)
+k_precompute_shift(const Affine<F>* __restrict__ prev, uint32_t n, int c, XYZZ<F>* __restrict__ scratch) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = load_vec(&prev[i]);
+  XYZZ<F> acc = XYZZ<F>::dbl_affine(p);
+  for (int k = 1; k < c; k++) acc = acc.dbl();
+  store_vec(&scratch[i], acc);
+}
+
+// XYZZ -> affine with Montgomery's simultaneous inversion over BATCH points per thread
+template <class F, int BATCH>
+__global__ void __launch_bounds__(128)
+k_batch_to_affine(const XYZZ<F>* __restrict__ src, uint32_t n, Affine<F>* __restrict__ dst) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t first = t * BATCH;
+  if (first >= n) return;
+  uint32_t cnt = min((uint32_t)BATCH, n - first);
+  // prefix products of ZZZ (identity points contribute 1); prefixes parked in dst[].x
+  F run = F::one();
+  for (uint32_t j = 0; j < cnt; j++) {
+    F zzz = load_vec_rw(&src[first + j].ZZZ);
+    store_vec(&dst[first + j].x, run);
+    if (!zzz.is_zero()) run = run * zzz;
+  }
+  F inv = run.inverse();
+  for (int j = (int)cnt - 1; j >= 0; j--) {
+    XYZZ<F> p = load_vec_rw(&src[first + j]);
+    Affine<F> a;
+    if (p.is_inf()) {
+      a = Affine<F>::inf();
+    } else {
+      F prefix = load_vec_rw(&dst[first + j].x);
+      F izzz = inv * prefix;   // 1 / ZZZ_j
+      inv = inv * p.ZZZ;       // drop ZZZ_j from the running inverse
+      F iz = izzz * p.ZZ;
+      F izz = iz.sqr();
+      a.x = p.X * izz;
+      a.y = p.Y * izzz;
+    }
+    store_vec(&dst[first + j], a);
+  }
+}
+
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------
+template <class T>
+struct BaseTable {
+  typedef typename T::F F;
+  uint32_t n = 0;
+  bool precomputed = false;
+  MsmConfig cfg{};
+  DevBuf<Affine<F>> pts;     // n points, or W * n when precomputed (window-major)
+  DevBuf<uint8_t> skip;      // 1 = identity base
+  // workspace (reused by every MSM on this table; calls on one table are stream-ordered)
+  DevBuf<uint32_t> counts, offsets, cursor, tile_sums, entries;
+  DevBuf<XYZZ<F>> parts, chunk_out, window_sums;
+
+  static MsmConfig choose_config(uint32_t n, bool precompute, int force_c);
+  void load(const uint8_t* host_raw, const uint8_t* host_inf, uint32_t n, bool precompute, int force_c,
+            cudaStream_t st);
+  void load_device_affine(const Affine<F>* d_affine, uint32_t n, bool precompute, int force_c, cudaStream_t st);
+  void build_tables(cudaStream_t st);
+  // d_scalars: count * 32 B canonical little-endian; uses bases [0, count); result -> d_result (XYZZ)
+  void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, cudaStream_t st);
+  size_t device_bytes() const;
+};
+
+template <class T>
+void finalize_points(const XYZZ<typename T::F>* d_results, int count, uint8_t* d_out, cudaStream_t st);
+
+}  // namespace zk

@@ -1,0 +1,140 @@
+// extern "C" bodies for one group (included by msm_g1.cu and msm_g2.cu with T fixed).
+#pragma once
+#include "msm_impl.cuh"
+#include "runtime.cuh"
+
+namespace zk {
+
+template <class T>
+struct TableHandle : HandleBase {
+  BaseTable<T> table;
+  DevBuf<uint32_t> d_scalars;            // staging for host-scalar calls
+  DevBuf<XYZZ<typename T::F>> d_result;  // one XYZZ result
+  DevBuf<uint8_t> d_out;                 // RAW + COMP bytes
+  DevBuf<int> d_err;
+  TableHandle() { kind = T::ID; }
+};
+
+// scalars must be canonical (< r): checked on the device for host-facing calls
+__global__ void k_check_scalars(const uint32_t* __restrict__ scalars, uint32_t n, int* __restrict__ err);
+
+template <class T>
+int api_table_load(const uint8_t* bases, const uint8_t* inf_flags, size_t n, int precompute, int window_bits,
+                   uint64_t* handle) {
+  ZK_API_BEGIN
+  ZK_REQUIRE(bases && handle && n > 0 && n < (1ull << 28), ZK_EARG, "table_load: bad arguments");
+  auto h = std::make_unique<TableHandle<T>>();
+  h->table.load(bases, inf_flags, (uint32_t)n, precompute != 0, window_bits, default_stream());
+  h->d_result.alloc(1);
+  h->d_out.alloc(T::RAW + T::COMP);
+  h->d_err.alloc(1);
+  *handle = register_handle(std::move(h));
+  ZK_API_END
+}
+
+template <class T>
+void table_msm_host(TableHandle<T>* h, const uint8_t* scalars, size_t n, uint8_t* out) {
+  cudaStream_t st = default_stream();
+  ZK_REQUIRE(scalars && out && n > 0 && n <= h->table.n, ZK_EARG, "msm: scalar count out of range");
+  h->d_scalars.ensure(n * 8);
+  ZK_CUDA(cudaMemcpyAsync(h->d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st));
+  k_check_scalars<<<cdiv(n, 256), 256, 0, st>>>(h->d_scalars.p, (uint32_t)n, h->d_err.p);
+  h->table.run(h->d_scalars.p, (uint32_t)n, h->d_result.p, st);
+  finalize_points<T>(h->d_result.p, 1, h->d_out.p, st);
+  int err = 0;
+  ZK_CUDA(cudaMemcpyAsync(out, h->d_out.p, T::RAW + T::COMP, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(err == 0, ZK_EPOINT, "msm: scalar is not canonical (>= r)");
+}
+
+template <class T>
+int api_table_msm(uint64_t handle, const uint8_t* scalars, size_t n, uint8_t* out) {
+  ZK_API_BEGIN
+  auto* h = static_cast<TableHandle<T>*>(lookup_handle(handle, T::ID));
+  table_msm_host<T>(h, scalars, n, out);
+  ZK_API_END
+}
+
+template <class T>
+int api_table_msm_dev(uint64_t handle, const void* d_scalars, size_t n, void* d_out, void* stream) {
+  ZK_API_BEGIN
+  auto* h = static_cast<TableHandle<T>*>(lookup_handle(handle, T::ID));
+  ZK_REQUIRE(d_scalars && d_out && n > 0 && n <= h->table.n, ZK_EARG, "msm_dev: bad arguments");
+  cudaStream_t st = stream ? (cudaStream_t)stream : default_stream();
+  h->table.run((const uint32_t*)d_scalars, (uint32_t)n, h->d_result.p, st);
+  finalize_points<T>(h->d_result.p, 1, (uint8_t*)d_out, st);
+  ZK_API_END
+}
+
+template <class T>
+int api_msm_oneshot(const uint8_t* bases, const uint8_t* inf_flags, const uint8_t* scalars, size_t n, uint8_t* out) {
+  ZK_API_BEGIN
+  ZK_REQUIRE(out, ZK_EARG, "msm: null output");
+  if (n == 0) {  // empty sum = identity (curve.ml:91 folds from zero)
+    memset(out, 0, T::RAW + T::COMP);
+    out[0] = 0x40;
+    out[T::RAW] = 0xc0;
+    return ZK_OK;
+  }
+  ZK_REQUIRE(bases && scalars && n < (1ull << 28), ZK_EARG, "msm: bad arguments");
+  TableHandle<T> h;
+  h.table.load(bases, inf_flags, (uint32_t)n, false, 0, default_stream());
+  h.d_result.alloc(1);
+  h.d_out.alloc(T::RAW + T::COMP);
+  h.d_err.alloc(1);
+  table_msm_host<T>(&h, scalars, n, out);
+  ZK_API_END
+}
+
+// out[i] = scalars[i] * generator, uncompressed
+template <class T>
+__global__ void __launch_bounds__(128)
+k_fixed_base(const uint32_t* __restrict__ scalars, uint32_t n, XYZZ<typename T::F>* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[8];
+  for (int j = 0; j < 8; j++) k[j] = scalars[8 * (size_t)i + j];
+  XYZZ<typename T::F> g = XYZZ<typename T::F>::from_affine(T::generator());
+  XYZZ<typename T::F> r = scalar_mul(g, k);
+  store_vec(&out[i], r);
+}
+template <class T>
+__global__ void __launch_bounds__(128)
+k_serialize_raw(const Affine<typename T::F>* __restrict__ pts, uint32_t n, uint8_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t buf[T::RAW + T::COMP];
+  Affine<typename T::F> p = load_vec_rw(&pts[i]);
+  T::serialize(p, buf);
+  for (int j = 0; j < T::RAW; j++) out[(size_t)i * T::RAW + j] = buf[j];
+}
+
+template <class T>
+int api_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out) {
+  ZK_API_BEGIN
+  ZK_REQUIRE(scalars && out && n > 0 && n < (1ull << 28), ZK_EARG, "fixed_base_mul: bad arguments");
+  typedef typename T::F F;
+  cudaStream_t st = default_stream();
+  DevBuf<uint32_t> d_s(n * 8);
+  DevBuf<XYZZ<F>> d_x(n);
+  DevBuf<Affine<F>> d_a(n);
+  DevBuf<uint8_t> d_o(n * T::RAW);
+  DevBuf<int> d_err(1);
+  ZK_CUDA(cudaMemcpyAsync(d_s.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+  k_check_scalars<<<cdiv(n, 256), 256, 0, st>>>(d_s.p, (uint32_t)n, d_err.p);
+  k_fixed_base<T><<<cdiv(n, 128), 128, 0, st>>>(d_s.p, (uint32_t)n, d_x.p);
+  k_batch_to_affine<F, 16><<<cdiv(cdiv(n, 16), 128), 128, 0, st>>>(d_x.p, (uint32_t)n, d_a.p);
+  k_serialize_raw<T><<<cdiv(n, 128), 128, 0, st>>>(d_a.p, (uint32_t)n, d_o.p);
+  ZK_CUDA(cudaGetLastError());
+  int err = 0;
+  ZK_CUDA(cudaMemcpyAsync(out, d_o.p, n * T::RAW, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(err == 0, ZK_EPOINT, "fixed_base_mul: scalar is not canonical (>= r)");
+  ZK_API_END
+}
+
+}  // namespace zk
