@@ -63,13 +63,16 @@ def msm_run(zk, group, logn, precompute, iters, c, seed=0x5A554B45):
     sc_w = rand_scalars(n, seed)
     d_sc = torch.from_numpy(sc_w.view(np.int64)).cuda()
     d_out = torch.zeros(outn, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
     times = []
     for it in range(iters + 1):
+      with torch.cuda.stream(side):
+        stream = side.cuda_stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(side)
         _lib.check(msm_dev(h.value, d_sc.data_ptr(), n, d_out.data_ptr(), stream))
-        e1.record()
+        e1.record(side)
         torch.cuda.synchronize()
         if it:
             times.append(e0.elapsed_time(e1))
