@@ -88,6 +88,83 @@ int zk_table_free(uint64_t handle);
 int zk_g1_fixed_base_mul(const uint8_t *scalars, size_t n, uint8_t *out);
 int zk_g2_fixed_base_mul(const uint8_t *scalars, size_t n, uint8_t *out);
 
+/* ---- QAP evaluation -----------------------------------------------------------------
+ * Replaces QAP.Make(F).eval (/root/reference/src/lib/zk/QAP.ml:120-135): with
+ * V = sum_k sol_k v_k, W, Y likewise, returns h with h * target = V W - Y.
+ * zk_qap_load uploads the dense QAP.t (QAP.ml:11-16): v, w, y are m x n row-major
+ * matrices of Fr (row k = coefficients of variable k's polynomial, lowest degree first,
+ * zero padded to n = degree(target)); target has n + 1 coefficients.
+ * zk_qap_eval: sol = m scalars in the same variable order; h_out (nullable) receives n - 1
+ * coefficients; vwy_out (nullable) receives V | W | Y, n coefficients each.
+ * Returns ZK_EREMAINDER where the reference's `assert (is_zero rem)` (QAP.ml:134) fails. */
+int zk_qap_load(const uint8_t *v, const uint8_t *w, const uint8_t *y, const uint8_t *target, size_t m,
+                size_t n, uint64_t *handle);
+int zk_qap_eval(uint64_t handle, const uint8_t *sol, uint8_t *h_out, uint8_t *vwy_out);
+int zk_qap_free(uint64_t handle);
+/* Polynomial.div_rem specialised to the exact quotient (polynomial.ml:142-169):
+ * h = (V W - Y) / T for coefficient vectors V, W, Y (n each) and T (n + 1); h_out gets n - 1. */
+int zk_fr_quotient(const uint8_t *V, const uint8_t *W, const uint8_t *Y, const uint8_t *T, size_t n,
+                   uint8_t *h_out);
+
+/* Target-only domain (no dense matrices) for zk_groth16_prove_coeffs; freed with zk_qap_free. */
+int zk_quotient_domain_load(const uint8_t *target, size_t n, uint64_t *handle);
+
+/* ---- Groth16 ---------------------------------------------------------------------------
+ * The proving key of /root/reference/src/groth16/groth16.ml:24-34, flattened.  Var.Map fields
+ * are given as arrays in increasing Var order; mid_index[j] is the position of the j-th
+ * mid variable in the witness vector (which lists ALL variables in increasing Var order). */
+typedef struct {
+  size_t n;                  /* degree of target = number of gates */
+  size_t m;                  /* number of variables = witness length */
+  size_t n_mid;              /* |Dom(ltd_mid)| */
+  const uint32_t *mid_index; /* n_mid entries */
+  const uint8_t *a, *b1, *d1;   /* G1: alpha, beta, delta            (ZK_G1_RAW each) */
+  const uint8_t *b2, *d2;       /* G2: beta, delta                   (ZK_G2_RAW each) */
+  const uint8_t *ti1;           /* G1: tau^i, at least n points      (groth16.ml:73 has n + 2) */
+  const uint8_t *ti2;           /* G2: tau^i, at least n points      (groth16.ml:87) */
+  const uint8_t *tiztd;         /* G1: tau^i Z(tau)/delta, n - 1     (groth16.ml:80-83) */
+  const uint8_t *ltd_mid;       /* G1: L_k(tau)/delta, n_mid points  (groth16.ml:74-79) */
+} zk_groth16_pkey;
+
+#define ZK_GROTH16_PROOF_OUT (ZK_G1_OUT + ZK_G2_OUT + ZK_G1_OUT) /* a | b | c point results */
+
+/* shard_index / shard_count: this process keeps slice shard_index of every list-valued field
+ * (SURVEY.md section 8e); with shard_count > 1 zk_groth16_prove returns this shard's PARTIAL
+ * sums, which the caller adds across shards (e.g. zk_g1_msm with unit scalars). */
+int zk_groth16_pk_load(const zk_groth16_pkey *pk, int shard_index, int shard_count, uint64_t *handle);
+/* Groth16.Make(C).prove (groth16.ml:235-237 then 123-161).  sol: m witness scalars; r, s: the two
+ * Fr.gen draws of groth16.ml:124-125 (r first), supplied by the host RNG. */
+int zk_groth16_prove(uint64_t pk, uint64_t qap, const uint8_t *sol, const uint8_t r[32], const uint8_t s[32],
+                     uint8_t proof_out[ZK_GROTH16_PROOF_OUT]);
+/* Same with the combinations V | W | Y given directly (3 * n scalars); `qap` may be a
+ * zk_quotient_domain_load handle.  Used when the dense QAP.t cannot exist. */
+int zk_groth16_prove_coeffs(uint64_t pk, uint64_t qap, const uint8_t *vwy, const uint8_t *sol,
+                            const uint8_t r[32], const uint8_t s[32], uint8_t proof_out[ZK_GROTH16_PROOF_OUT]);
+
+/* ---- Pinocchio (Protocol 2) --------------------------------------------------------------
+ * The proving key of /root/reference/src/pinocchio/pinocchio.ml:37-60, flattened as above.
+ * `one` is G1.one (used by ZKCompute.f's "- one * dy", pinocchio.ml:485). */
+typedef struct {
+  size_t n, m, n_mid;
+  const uint32_t *mid_index;
+  const uint8_t *vv, *yy, *vav, *yay, *bvwy; /* G1, n_mid points each */
+  const uint8_t *ww, *waw;                   /* G2, n_mid points each */
+  const uint8_t *si;                         /* G1, n + 1 points (pinocchio.ml:133) */
+  const uint8_t *v_all, *w_all;              /* G1, m points each */
+  const uint8_t *one, *vt, *yt, *vavt, *yayt, *vbt, *wbt, *ybt; /* G1 single points */
+  const uint8_t *wt, *wawt;                  /* G2 single points */
+} zk_pinocchio_pkey;
+
+#define ZK_PINOCCHIO_PROOF_OUT (6 * ZK_G1_OUT + 2 * ZK_G2_OUT)
+
+int zk_pinocchio_pk_load(const zk_pinocchio_pkey *pk, int shard_index, int shard_count, uint64_t *handle);
+/* d = dv | dw | dy (3 * 32 B, the draws of pinocchio.ml:428-430) selects ZK.prove (:559-561);
+ * d = NULL selects NonZK.prove (:536-538).  proof_out holds vv | ww | yy | h | vavv | waww |
+ * yayy | bvwy point results (record order of pinocchio.ml:195-208). */
+int zk_pinocchio_prove(uint64_t pk, uint64_t qap, const uint8_t *sol, const uint8_t *d,
+                       uint8_t proof_out[ZK_PINOCCHIO_PROOF_OUT]);
+int zk_key_free(uint64_t handle);
+
 /* ---- measurement helpers --------------------------------------------------------
  * Integer-pipe microbenchmarks.  kind: 0 = mad.lo.u32 chains,
  * 1 = mad.lo.cc / madc.hi.cc carry chains, 2 = mad.wide.u32, 3 = Fp Montgomery products

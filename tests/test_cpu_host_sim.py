@@ -1,0 +1,121 @@
+"""Host simulation of the device limb algorithms: the SAME headers the kernels use
+(mont.cuh, ec.cuh) compiled by g++ with -DZK_HOST_SIM, where ptx.cuh emulates each PTX carry
+instruction.  A development check of the formulas on the CPU — tests only, never shipped."""
+import ctypes
+import os
+import random
+import subprocess
+import tempfile
+
+import pytest
+
+from oracle.bls12_381 import G1, G2, P, R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "host_sim")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    out = tempfile.mkdtemp(prefix="zk_host_sim_")
+    libs = {}
+    for name in ("sim_field", "sim_ec"):
+        so = os.path.join(out, name + ".so")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DZK_HOST_SIM", "-shared", "-fPIC", "-x", "c++",
+                               os.path.join(SIM, name + ".cpp"), "-o", so])
+        libs[name] = ctypes.CDLL(so)
+    return libs
+
+
+def _field(fn, n, op, a, b=0):
+    A = (ctypes.c_uint32 * n)(*[(a >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+    B = (ctypes.c_uint32 * n)(*[(b >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+    Out = (ctypes.c_uint32 * n)()
+    fn(op, A, B, Out)
+    return sum(int(Out[i]) << (32 * i) for i in range(n))
+
+
+@pytest.mark.parametrize("which,mod,n", [("sim_fp_op", P, 12), ("sim_fr_op", R, 8)])
+def test_montgomery_limb_algorithms(sim, which, mod, n):
+    fn = getattr(sim["sim_field"], which)
+    rng = random.Random(5)
+    Rm = 1 << (32 * n)
+    Ri = pow(Rm, -1, mod)
+    vals = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, Rm % mod] + [rng.randrange(mod) for _ in range(150)]
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        assert _field(fn, n, 0, a, b) == a * b * Ri % mod
+        assert _field(fn, n, 1, a, b) == (a + b) % mod
+        assert _field(fn, n, 2, a, b) == (a - b) % mod
+        assert _field(fn, n, 3, a) == (-a) % mod
+        assert _field(fn, n, 4, a) == a * Rm % mod
+        assert _field(fn, n, 5, a) == a * Ri % mod
+    for a in vals[:10]:
+        assert _field(fn, n, 6, a * Rm % mod) == ((pow(a, -1, mod) * Rm % mod) if a else 0)
+
+
+RM = (1 << 384) % P
+
+
+def _fpl(x):
+    x = x * RM % P
+    return [(x >> (32 * i)) & 0xFFFFFFFF for i in range(12)]
+
+
+def _unfp(l):
+    return sum(int(v) << (32 * i) for i, v in enumerate(l)) * pow(RM, -1, P) % P
+
+
+def _enc_f(G, c):
+    return _fpl(c) if G is G1 else _fpl(c[0]) + _fpl(c[1])
+
+
+def _dec_f(G, l):
+    return _unfp(l) if G is G1 else (_unfp(l[:12]), _unfp(l[12:]))
+
+
+def _enc_aff(G, pt, w):
+    return [0] * (2 * w) if pt is None else _enc_f(G, pt[0]) + _enc_f(G, pt[1])
+
+
+def _enc_xyzz(G, pt, z, w):
+    if pt is None:
+        return [0] * (4 * w)
+    F = G.F
+    zf = z if G is G1 else (z, (z * 7 + 1) % P)
+    zz = F.mul(zf, zf)
+    zzz = F.mul(zz, zf)
+    return _enc_f(G, F.mul(pt[0], zz)) + _enc_f(G, F.mul(pt[1], zzz)) + _enc_f(G, zz) + _enc_f(G, zzz)
+
+
+def _ec(sim, G, op, a, b, k=0):
+    w = 12 if G is G1 else 24
+    fn = sim["sim_ec"].sim_g1_op if G is G1 else sim["sim_ec"].sim_g2_op
+    A = (ctypes.c_uint32 * (4 * w))(*a)
+    B = (ctypes.c_uint32 * (4 * w))(*(b + [0] * (4 * w - len(b))))
+    K = (ctypes.c_uint32 * 8)(*[(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+    Out = (ctypes.c_uint32 * (6 * w))()
+    fn(op, A, B, K, Out)
+    o = list(Out)
+    x, y = _dec_f(G, o[:w]), _dec_f(G, o[w:2 * w])
+    zero = 0 if G is G1 else (0, 0)
+    return None if (x == zero and y == zero) else (x, y)
+
+
+@pytest.mark.parametrize("G", [G1, G2], ids=["G1", "G2"])
+def test_xyzz_formulas(sim, G):
+    w = 12 if G is G1 else 24
+    rng = random.Random(9)
+    pts = [None] + [G.mul(G.one, rng.randrange(1, R)) for _ in range(4)]
+    for p in pts:
+        for q in pts:
+            z = rng.randrange(1, P)
+            assert _ec(sim, G, 0, _enc_xyzz(G, p, z, w), _enc_aff(G, q, w)) == G.add(p, q)
+            assert _ec(sim, G, 1, _enc_xyzz(G, p, z, w), _enc_xyzz(G, q, z + 3, w)) == G.add(p, q)
+        z = rng.randrange(1, P)
+        assert _ec(sim, G, 0, _enc_xyzz(G, p, z, w), _enc_aff(G, p, w)) == G.add(p, p)          # P + P
+        assert _ec(sim, G, 0, _enc_xyzz(G, p, z, w), _enc_aff(G, G.neg(p), w)) is None           # P - P
+        assert _ec(sim, G, 1, _enc_xyzz(G, p, z, w), _enc_xyzz(G, G.neg(p), z + 5, w)) is None
+        assert _ec(sim, G, 2, _enc_xyzz(G, p, z, w), []) == G.add(p, p)
+    for k in (0, 1, R - 1, rng.randrange(R)):
+        assert _ec(sim, G, 3, _enc_xyzz(G, pts[1], 12345, w), [], k) == G.mul(pts[1], k)

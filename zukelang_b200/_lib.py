@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libzkb200.so")
 
 ZK_OK, ZK_EARG, ZK_EPOINT, ZK_ECUDA, ZK_EREMAINDER = 0, -1, -2, -3, -4
 FR_BYTES, G1_RAW, G1_COMP, G1_OUT, G2_RAW, G2_COMP, G2_OUT = 32, 96, 48, 144, 192, 96, 288
+GROTH16_PROOF_OUT = G1_OUT + G2_OUT + G1_OUT
+PINOCCHIO_PROOF_OUT = 6 * G1_OUT + 2 * G2_OUT
 
 
 class ZkError(RuntimeError):
@@ -46,9 +48,36 @@ SIGNATURES = {
     "zk_table_free": (c_int, [c_uint64]),
     "zk_g1_fixed_base_mul": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_g2_fixed_base_mul": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "zk_qap_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, POINTER(c_uint64)]),
+    "zk_quotient_domain_load": (c_int, [c_void_p, c_size_t, POINTER(c_uint64)]),
+    "zk_qap_eval": (c_int, [c_uint64, c_void_p, c_void_p, c_void_p]),
+    "zk_qap_free": (c_int, [c_uint64]),
+    "zk_fr_quotient": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "zk_groth16_pk_load": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64)]),
+    "zk_groth16_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zk_groth16_prove_coeffs": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zk_pinocchio_pk_load": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64)]),
+    "zk_pinocchio_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),
+    "zk_key_free": (c_int, [c_uint64]),
     "zk_bench_intpipe": (c_int, [c_int, c_int, POINTER(c_double), POINTER(c_double)]),
     "zk_test_field_op": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
 }
+
+class Groth16PKeyStruct(ctypes.Structure):
+    """zk_groth16_pkey of include/zkb200.h."""
+    _fields_ = [("n", c_size_t), ("m", c_size_t), ("n_mid", c_size_t), ("mid_index", c_void_p),
+                ("a", c_void_p), ("b1", c_void_p), ("d1", c_void_p), ("b2", c_void_p), ("d2", c_void_p),
+                ("ti1", c_void_p), ("ti2", c_void_p), ("tiztd", c_void_p), ("ltd_mid", c_void_p)]
+
+
+class PinocchioPKeyStruct(ctypes.Structure):
+    """zk_pinocchio_pkey of include/zkb200.h."""
+    _fields_ = [("n", c_size_t), ("m", c_size_t), ("n_mid", c_size_t), ("mid_index", c_void_p),
+                ("vv", c_void_p), ("yy", c_void_p), ("vav", c_void_p), ("yay", c_void_p), ("bvwy", c_void_p),
+                ("ww", c_void_p), ("waw", c_void_p), ("si", c_void_p), ("v_all", c_void_p), ("w_all", c_void_p),
+                ("one", c_void_p), ("vt", c_void_p), ("yt", c_void_p), ("vavt", c_void_p), ("yayt", c_void_p),
+                ("vbt", c_void_p), ("wbt", c_void_p), ("ybt", c_void_p), ("wt", c_void_p), ("wawt", c_void_p)]
+
 
 _lib = None
 _initialised = False

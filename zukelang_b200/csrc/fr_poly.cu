@@ -1,0 +1,443 @@
+// Fr polynomial kernels and the QAP quotient (see fr_poly.cuh for the algorithm note).
+#include "fr_poly.cuh"
+#include "runtime.cuh"
+
+namespace zk {
+
+// ---------------------------------------------------------------------------
+// small vector kernels
+// ---------------------------------------------------------------------------
+static __global__ void k_fr_to_mont(const uint32_t* __restrict__ raw, Fr* __restrict__ out, uint32_t n, int* err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr a = load_vec(reinterpret_cast<const Fr*>(raw) + i);
+  if (!a.is_canonical_raw()) { if (err) atomicExch(err, 1); a = Fr::zero(); }
+  store_vec(&out[i], a.to_mont());
+}
+static __global__ void k_fr_from_mont(const Fr* __restrict__ in, uint32_t* __restrict__ raw, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr a = load_vec_rw(&in[i]);
+  store_vec(reinterpret_cast<Fr*>(raw) + i, a.from_mont());
+}
+static __global__ void k_fr_axpby(const Fr* a, const Fr* __restrict__ x, const Fr* b, const Fr* __restrict__ y,
+                                  Fr* __restrict__ out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr r = load_vec_rw(a) * load_vec_rw(&x[i]);
+  if (y) r = r + load_vec_rw(b) * load_vec_rw(&y[i]);
+  store_vec(&out[i], r);
+}
+
+void fr_to_mont(const uint32_t* d_raw, Fr* d_out, uint32_t n, int* d_err, cudaStream_t st) {
+  if (n) k_fr_to_mont<<<cdiv(n, 256), 256, 0, st>>>(d_raw, d_out, n, d_err);
+}
+void fr_from_mont(const Fr* d_in, uint32_t* d_raw, uint32_t n, cudaStream_t st) {
+  if (n) k_fr_from_mont<<<cdiv(n, 256), 256, 0, st>>>(d_in, d_raw, n);
+}
+void fr_axpby(const Fr* a, const Fr* x, const Fr* b, const Fr* y, Fr* out, uint32_t n, cudaStream_t st) {
+  if (n) k_fr_axpby<<<cdiv(n, 256), 256, 0, st>>>(a, x, b, y, out, n);
+}
+
+__device__ __noinline__ Fr fr_pow_u32(const Fr& base, uint32_t e) {
+  Fr acc = Fr::one();
+  if (e == 0) return acc;
+  int top = 31 - __clz(e);
+  for (int bit = top; bit >= 0; bit--) {
+    acc = acc * acc;
+    if ((e >> bit) & 1) acc = acc * base;
+  }
+  return acc;
+}
+
+// consts[0] = omega_D, [1] = omega_D^-1, [2] = g, [3] = g^-1, [4] = 1/D   (Montgomery)
+static __global__ void k_ntt_consts(int logD, Fr* consts) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr w, wi, g, gi, i2;
+  for (int i = 0; i < 8; i++) {
+    w.v[i] = FrParams::root32(i); wi.v[i] = FrParams::root32_inv(i);
+    g.v[i] = FrParams::gen7(i); gi.v[i] = FrParams::gen7_inv(i); i2.v[i] = FrParams::inv2(i);
+  }
+  for (int i = logD; i < 32; i++) { w = w * w; wi = wi * wi; }
+  Fr dinv = Fr::one();
+  for (int i = 0; i < logD; i++) dinv = dinv * i2;
+  consts[0] = w; consts[1] = wi; consts[2] = g; consts[3] = gi; consts[4] = dinv;
+}
+
+// out[i] = scale * base^i, 64 consecutive powers per thread
+static __global__ void k_fr_powers(const Fr* base, const Fr* scale, Fr* __restrict__ out, uint32_t n) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i0 = t * 64;
+  if (i0 >= n) return;
+  Fr b = load_vec_rw(base);
+  Fr p = fr_pow_u32(b, i0);
+  if (scale) p = p * load_vec_rw(scale);
+  uint32_t end = min(n, i0 + 64);
+  for (uint32_t i = i0; i < end; i++) {
+    store_vec(&out[i], p);
+    p = p * b;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// radix-2 NTT stages (gridDim.y = number of vectors, each D long and contiguous)
+// ---------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+k_ntt_dif_stage(Fr* __restrict__ x, const Fr* __restrict__ tw, uint32_t D, int logHalf, int s) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= D / 2) return;
+  Fr* v = x + (size_t)blockIdx.y * D;
+  uint32_t half = 1u << logHalf;
+  uint32_t j = t & (half - 1);
+  uint32_t i0 = ((t >> logHalf) << (logHalf + 1)) + j;
+  uint32_t i1 = i0 + half;
+  Fr a = load_vec_rw(&v[i0]), b = load_vec_rw(&v[i1]);
+  Fr w = load_vec(&tw[(size_t)j << s]);
+  store_vec(&v[i0], a + b);
+  store_vec(&v[i1], (a - b) * w);
+}
+static __global__ void __launch_bounds__(256)
+k_ntt_dit_stage(Fr* __restrict__ x, const Fr* __restrict__ tw_inv, uint32_t D, int logHalf, int s) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= D / 2) return;
+  Fr* v = x + (size_t)blockIdx.y * D;
+  uint32_t half = 1u << logHalf;
+  uint32_t j = t & (half - 1);
+  uint32_t i0 = ((t >> logHalf) << (logHalf + 1)) + j;
+  uint32_t i1 = i0 + half;
+  Fr a = load_vec_rw(&v[i0]);
+  Fr b = load_vec_rw(&v[i1]) * load_vec(&tw_inv[(size_t)j << s]);
+  store_vec(&v[i0], a + b);
+  store_vec(&v[i1], a - b);
+}
+
+void NttPlan::build(int logD_, cudaStream_t st) {
+  ZK_REQUIRE(logD_ >= 1 && logD_ <= 28, ZK_EARG, "NTT size out of range");
+  logD = logD_;
+  D = 1u << logD;
+  DevBuf<Fr> consts(5);
+  k_ntt_consts<<<1, 1, 0, st>>>(logD, consts.p);
+  tw.alloc(D / 2);
+  tw_inv.alloc(D / 2);
+  coset.alloc(D);
+  coset_inv.alloc(D);
+  k_fr_powers<<<cdiv(cdiv(D / 2, 64), 128), 128, 0, st>>>(consts.p + 0, nullptr, tw.p, D / 2);
+  k_fr_powers<<<cdiv(cdiv(D / 2, 64), 128), 128, 0, st>>>(consts.p + 1, nullptr, tw_inv.p, D / 2);
+  k_fr_powers<<<cdiv(cdiv(D, 64), 128), 128, 0, st>>>(consts.p + 2, nullptr, coset.p, D);
+  k_fr_powers<<<cdiv(cdiv(D, 64), 128), 128, 0, st>>>(consts.p + 3, consts.p + 4, coset_inv.p, D);
+  ZK_CUDA(cudaGetLastError());
+  ZK_CUDA(cudaStreamSynchronize(st));  // consts is freed on return
+}
+
+static void ntt_forward_batch(const NttPlan& p, Fr* d, int batch, cudaStream_t st) {
+  dim3 grid(cdiv(p.D / 2, 256), batch);
+  for (int s = 0; s < p.logD; s++) k_ntt_dif_stage<<<grid, 256, 0, st>>>(d, p.tw.p, p.D, p.logD - 1 - s, s);
+}
+static void ntt_inverse_batch(const NttPlan& p, Fr* d, int batch, cudaStream_t st) {
+  dim3 grid(cdiv(p.D / 2, 256), batch);
+  for (int s = p.logD - 1; s >= 0; s--) k_ntt_dit_stage<<<grid, 256, 0, st>>>(d, p.tw_inv.p, p.D, p.logD - 1 - s, s);
+}
+void NttPlan::forward(Fr* d, cudaStream_t st) const { ntt_forward_batch(*this, d, 1, st); }
+void NttPlan::inverse(Fr* d, cudaStream_t st) const { ntt_inverse_batch(*this, d, 1, st); }
+
+// ---------------------------------------------------------------------------
+// QAP kernels
+// ---------------------------------------------------------------------------
+// QAP.ml:121-131 eval':  out[i] = sum_k sol[k] * M[k][i]; blockIdx.y selects V / W / Y.
+// Writes the n coefficients to coeffs (kept for the MSM scalars) and a zero-padded,
+// coset-shifted copy of length D to work (input of the forward NTT).
+static __global__ void __launch_bounds__(128)
+k_qap_combine(const Fr* __restrict__ vm, const Fr* __restrict__ wm, const Fr* __restrict__ ym,
+              const Fr* __restrict__ sol, uint32_t m, uint32_t n, uint32_t D, const Fr* __restrict__ coset,
+              Fr* __restrict__ coeffs, Fr* __restrict__ work) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  int which = blockIdx.y;
+  Fr acc = Fr::zero();
+  if (i < n) {
+    const Fr* M = which == 0 ? vm : (which == 1 ? wm : ym);
+    for (uint32_t k = 0; k < m; k++) {
+      Fr s = load_vec(&sol[k]);
+      if (s.is_zero()) continue;
+      acc = acc + s * load_vec(&M[(size_t)k * n + i]);
+    }
+    store_vec(&coeffs[(size_t)which * n + i], acc);
+    acc = acc * load_vec(&coset[i]);
+  }
+  store_vec(&work[(size_t)which * D + i], acc);
+}
+
+// zero-padded coset shift of an n-coefficient vector into a D-long work vector
+static __global__ void k_coset_load(const Fr* __restrict__ coeffs, uint32_t n, uint32_t D,
+                                    const Fr* __restrict__ coset, Fr* __restrict__ work) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  Fr a = Fr::zero();
+  if (i < n) a = load_vec_rw(&coeffs[i]) * load_vec(&coset[i]);
+  store_vec(&work[i], a);
+}
+
+// in-place inversion, 16 elements per thread (Montgomery's trick); a zero raises the flag
+static __global__ void k_fr_batch_inverse(Fr* __restrict__ x, uint32_t n, int* flag) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i0 = t * 16;
+  if (i0 >= n) return;
+  uint32_t cnt = min(16u, n - i0);
+  Fr pre[16];
+  Fr run = Fr::one();
+  for (uint32_t j = 0; j < cnt; j++) {
+    Fr a = load_vec_rw(&x[i0 + j]);
+    if (a.is_zero()) { atomicExch(flag, 1); a = Fr::one(); }
+    pre[j] = run;
+    run = run * a;
+  }
+  Fr inv = run.inverse();
+  for (int j = (int)cnt - 1; j >= 0; j--) {
+    Fr a = load_vec_rw(&x[i0 + j]);
+    if (a.is_zero()) a = Fr::one();
+    store_vec(&x[i0 + j], inv * pre[j]);
+    inv = inv * a;
+  }
+}
+
+// H[j] = (V[j] W[j] - Y[j]) / t[j] on the coset
+static __global__ void k_quotient_pointwise(const Fr* __restrict__ work, uint32_t D, const Fr* __restrict__ t_inv,
+                                            Fr* __restrict__ H) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  Fr v = load_vec_rw(&work[j]), w = load_vec_rw(&work[(size_t)D + j]), y = load_vec_rw(&work[2 * (size_t)D + j]);
+  store_vec(&H[j], (v * w - y) * load_vec(&t_inv[j]));
+}
+static __global__ void k_fr_mul_inplace(Fr* __restrict__ x, const Fr* __restrict__ y, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store_vec(&x[i], load_vec_rw(&x[i]) * load_vec(&y[i]));
+}
+
+// Divisibility check (QAP.ml:134 `assert (is_zero rem)`): evaluate V, W, Y, t and h at a fixed
+// point x0 outside the coset and compare h(x0) t(x0) with V(x0) W(x0) - Y(x0).
+struct EvalJob {
+  const Fr* coeffs[5];
+  uint32_t len[5];
+};
+constexpr int EVAL_CHUNK = 32, EVAL_THREADS = 256;
+static __device__ __forceinline__ Fr eval_point() {
+  // an arbitrary fixed element (Montgomery image of a constant); any point off the domain works
+  Fr x;
+  const uint32_t c[8] = {0x7f4a7c15u, 0x9e3779b9u, 0xf39cc060u, 0x5cedc834u, 0x1082276bu, 0xf3a8b2c1u, 0x2545f491u, 0x0f6c7d3au};
+  for (int i = 0; i < 8; i++) x.v[i] = c[i];
+  return x;
+}
+static __global__ void __launch_bounds__(EVAL_THREADS)
+k_poly_eval_partial(EvalJob job, Fr* __restrict__ partials, uint32_t blocks_per_poly) {
+  __shared__ Fr sm[EVAL_THREADS];
+  int which = blockIdx.y;
+  const Fr* c = job.coeffs[which];
+  uint32_t n = job.len[which];
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t i0 = t * EVAL_CHUNK;
+  Fr acc = Fr::zero();
+  if (i0 < n) {
+    Fr x0 = eval_point();
+    uint32_t end = min(n, i0 + EVAL_CHUNK);
+    for (int i = (int)end - 1; i >= (int)i0; i--) acc = acc * x0 + load_vec_rw(&c[i]);
+    acc = acc * fr_pow_u32(x0, i0);
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[(size_t)which * blocks_per_poly + blockIdx.x] = sm[0];
+}
+static __global__ void k_poly_eval_check(const Fr* __restrict__ partials, uint32_t blocks_per_poly, int* flag) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr e[5];
+  for (int w = 0; w < 5; w++) {
+    Fr acc = Fr::zero();
+    for (uint32_t b = 0; b < blocks_per_poly; b++) acc = acc + load_vec_rw(&partials[(size_t)w * blocks_per_poly + b]);
+    e[w] = acc;
+  }
+  // order: V, W, Y, t, h
+  if (e[4] * e[3] != e[0] * e[1] - e[2]) atomicExch(flag, 1);
+}
+
+// ---------------------------------------------------------------------------
+// QapDevice
+// ---------------------------------------------------------------------------
+static int log2_ceil_u32(uint32_t n) {
+  int l = 0;
+  while ((1ull << l) < n) l++;
+  return l;
+}
+
+struct QuotientScratch {
+  DevBuf<Fr> work;  // 3 * D
+};
+
+void QapDevice::load(const uint8_t* v, const uint8_t* w, const uint8_t* y, const uint8_t* tgt, uint32_t m_, uint32_t n_,
+                     cudaStream_t st) {
+  ZK_REQUIRE(n_ >= 1 && (uint64_t)m_ * n_ < (1ull << 31), ZK_EARG, "qap_load: bad dimensions");
+  m = m_;
+  n = n_;
+  plan.build(log2_ceil_u32(n + 1) < 1 ? 1 : log2_ceil_u32(n + 1), st);
+  const uint32_t D = plan.D;
+  flag.alloc(2);
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
+  size_t mn = (size_t)m * n;
+  {
+    DevBuf<uint32_t> raw(mn * 8 > (size_t)(n + 1) * 8 ? mn * 8 : (size_t)(n + 1) * 8);
+    auto up = [&](const uint8_t* src, DevBuf<Fr>& dst, size_t count) {
+      dst.alloc(count);
+      if (!count) return;
+      ZK_CUDA(cudaMemcpyAsync(raw.p, src, count * 32, cudaMemcpyHostToDevice, st));
+      fr_to_mont(raw.p, dst.p, (uint32_t)count, flag.p, st);
+    };
+    if (m) { up(v, vm, mn); up(w, wm, mn); up(y, ym, mn); }
+    up(tgt, target, n + 1);
+    ZK_CUDA(cudaStreamSynchronize(st));
+  }
+  // 1 / t on the coset (bit-reversed, matching the forward transform's output order)
+  t_inv_evals.alloc(D);
+  k_coset_load<<<cdiv(D, 256), 256, 0, st>>>(target.p, n + 1, D, plan.coset.p, t_inv_evals.p);
+  plan.forward(t_inv_evals.p, st);
+  k_fr_batch_inverse<<<cdiv(cdiv(D, 16), 64), 64, 0, st>>>(t_inv_evals.p, D, flag.p + 1);
+  ZK_CUDA(cudaGetLastError());
+  int fl[2] = {0, 0};
+  ZK_CUDA(cudaMemcpyAsync(fl, flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "qap_load: coefficient is not canonical (>= r)");
+  ZK_REQUIRE(fl[1] == 0, ZK_EARG, "qap_load: target vanishes on the evaluation coset");
+  sol_m.alloc(m ? m : 1);
+  V.alloc(3 * (size_t)D);       // work: V | W | Y evaluations
+  H.alloc(D);
+  Vc.alloc(3 * (size_t)n);      // coefficient copies: V | W | Y, n each
+  uint32_t bpp = cdiv(cdiv(n + 1, EVAL_CHUNK), EVAL_THREADS);
+  partials.alloc(5 * (size_t)bpp);
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
+}
+
+void QapDevice::eval(const uint32_t* d_sol_raw, cudaStream_t st) {
+  const uint32_t D = plan.D;
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
+  fr_to_mont(d_sol_raw, sol_m.p, m, flag.p, st);
+  k_qap_combine<<<dim3(cdiv(D, 128), 3), 128, 0, st>>>(vm.p, wm.p, ym.p, sol_m.p, m, n, D, plan.coset.p, Vc.p, V.p);
+  quotient_from_work(st);
+}
+
+void QapDevice::quotient_from_work(cudaStream_t st) {
+  const uint32_t D = plan.D;
+  ntt_forward_batch(plan, V.p, 3, st);
+  k_quotient_pointwise<<<cdiv(D, 256), 256, 0, st>>>(V.p, D, t_inv_evals.p, H.p);
+  plan.inverse(H.p, st);
+  k_fr_mul_inplace<<<cdiv(D, 256), 256, 0, st>>>(H.p, plan.coset_inv.p, D);
+  // divisibility check at x0
+  EvalJob job;
+  job.coeffs[0] = Vc.p; job.len[0] = n;
+  job.coeffs[1] = Vc.p + n; job.len[1] = n;
+  job.coeffs[2] = Vc.p + 2 * (size_t)n; job.len[2] = n;
+  job.coeffs[3] = target.p; job.len[3] = n + 1;
+  job.coeffs[4] = H.p; job.len[4] = n > 0 ? n - 1 : 0;
+  uint32_t bpp = cdiv(cdiv(n + 1, EVAL_CHUNK), EVAL_THREADS);
+  k_poly_eval_partial<<<dim3(bpp, 5), EVAL_THREADS, 0, st>>>(job, partials.p, bpp);
+  k_poly_eval_check<<<1, 1, 0, st>>>(partials.p, bpp, flag.p + 1);
+  ZK_CUDA(cudaGetLastError());
+}
+
+void QapDevice::set_coeffs(const uint32_t* d_vwy_raw, cudaStream_t st) {
+  const uint32_t D = plan.D;
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
+  fr_to_mont(d_vwy_raw, Vc.p, 3 * n, flag.p, st);
+  for (int which = 0; which < 3; which++)
+    k_coset_load<<<cdiv(D, 256), 256, 0, st>>>(Vc.p + (size_t)which * n, n, D, plan.coset.p, V.p + (size_t)which * D);
+}
+
+}  // namespace zk
+
+extern "C" {
+
+int zk_qap_load(const uint8_t* v, const uint8_t* w, const uint8_t* y, const uint8_t* target, size_t m, size_t n,
+                uint64_t* handle) {
+  ZK_API_BEGIN
+  using namespace zk;
+  ZK_REQUIRE(v && w && y && target && handle && m > 0 && n > 0 && m < (1u << 28) && n < (1u << 27), ZK_EARG,
+             "qap_load: bad arguments");
+  auto h = std::make_unique<QapHandle>();
+  h->q.load(v, w, y, target, (uint32_t)m, (uint32_t)n, default_stream());
+  *handle = register_handle(std::move(h));
+  ZK_API_END
+}
+
+int zk_quotient_domain_load(const uint8_t* target, size_t n, uint64_t* handle) {
+  ZK_API_BEGIN
+  using namespace zk;
+  ZK_REQUIRE(target && handle && n >= 2 && n < (1u << 27), ZK_EARG, "quotient_domain_load: bad arguments");
+  auto h = std::make_unique<QapHandle>();
+  h->q.load(nullptr, nullptr, nullptr, target, 0, (uint32_t)n, default_stream());
+  *handle = register_handle(std::move(h));
+  ZK_API_END
+}
+
+int zk_qap_free(uint64_t handle) {
+  ZK_API_BEGIN
+  ZK_CUDA(cudaDeviceSynchronize());
+  zk::lookup_handle(handle, 3);
+  zk::drop_handle(handle);
+  ZK_API_END
+}
+
+// h: (n - 1) * 32 bytes out (nullable); vwy: 3 * n * 32 bytes out (nullable)
+int zk_qap_eval(uint64_t handle, const uint8_t* sol, uint8_t* h_out, uint8_t* vwy_out) {
+  ZK_API_BEGIN
+  using namespace zk;
+  auto* h = static_cast<QapHandle*>(lookup_handle(handle, 3));
+  QapDevice& q = h->q;
+  ZK_REQUIRE(sol, ZK_EARG, "qap_eval: null witness");
+  cudaStream_t st = default_stream();
+  size_t need = std::max((size_t)q.m * 8, 3 * (size_t)q.n * 8);
+  h->d_raw.ensure(need);
+  ZK_CUDA(cudaMemcpyAsync(h->d_raw.p, sol, (size_t)q.m * 32, cudaMemcpyHostToDevice, st));
+  q.eval(h->d_raw.p, st);
+  int fl[2];
+  ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  if (h_out && q.n > 1) {
+    fr_from_mont(q.H.p, h->d_raw.p, q.n - 1, st);
+    ZK_CUDA(cudaMemcpyAsync(h_out, h->d_raw.p, (size_t)(q.n - 1) * 32, cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+  }
+  if (vwy_out) {
+    fr_from_mont(q.Vc.p, h->d_raw.p, 3 * q.n, st);
+    ZK_CUDA(cudaMemcpyAsync(vwy_out, h->d_raw.p, 3 * (size_t)q.n * 32, cudaMemcpyDeviceToHost, st));
+  }
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "qap_eval: witness scalar is not canonical (>= r)");
+  ZK_REQUIRE(fl[1] == 0, ZK_EREMAINDER, "qap_eval: V*W - Y is not divisible by the target (QAP.ml:134)");
+  ZK_API_END
+}
+
+// Standalone quotient from coefficient vectors: V, W, Y of n coefficients, T of n + 1; h gets n - 1.
+int zk_fr_quotient(const uint8_t* V, const uint8_t* W, const uint8_t* Y, const uint8_t* T, size_t n, uint8_t* h_out) {
+  ZK_API_BEGIN
+  using namespace zk;
+  ZK_REQUIRE(V && W && Y && T && h_out && n >= 2 && n < (1u << 27), ZK_EARG, "fr_quotient: bad arguments");
+  cudaStream_t st = default_stream();
+  QapDevice q;
+  q.load(nullptr, nullptr, nullptr, T, 0, (uint32_t)n, st);
+  DevBuf<uint32_t> raw(3 * n * 8);
+  ZK_CUDA(cudaMemcpyAsync(raw.p, V, n * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(raw.p + n * 8, W, n * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(raw.p + 2 * n * 8, Y, n * 32, cudaMemcpyHostToDevice, st));
+  q.set_coeffs(raw.p, st);
+  q.quotient_from_work(st);
+  int fl[2];
+  ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  fr_from_mont(q.H.p, raw.p, (uint32_t)n - 1, st);
+  ZK_CUDA(cudaMemcpyAsync(h_out, raw.p, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "fr_quotient: coefficient is not canonical (>= r)");
+  ZK_REQUIRE(fl[1] == 0, ZK_EREMAINDER, "fr_quotient: V*W - Y is not divisible by T");
+  ZK_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,407 @@
+// Groth16 and Pinocchio provers on top of the MSM and QAP kernels.
+//
+// Replaces Groth16.Make(C).prove (/root/reference/src/groth16/groth16.ml:123-161, 235-237),
+// Pinocchio.Make(C).Compute.f (src/pinocchio/pinocchio.ml:210-248) and ZKCompute.f (:427-514).
+//
+// Every proof element is rewritten, by linearity, as ONE multi-scalar multiplication over a
+// resident base table made of the relevant proving-key fields; the single scalar
+// multiplications of the reference (d1 * r, a * s, b1 * r, vt * dv, ...) become extra
+// (base, scalar) pairs of those MSMs instead of 255-step double-and-add tails:
+//
+//   Groth16   A = [a, d1 | ti1] . [1, r | V]
+//             B = [b2, d2 | ti2] . [1, s | W]
+//             C = [a, b1, d1 | ti1 | tiztd | ltd_mid] . [s, r, r s | s V + r W | h | w_mid]
+//   (C = L + H + s A + r B1 - r s d1 with A, B1 expanded; groth16.ml:154-159.)
+//
+// The group elements — and so the serialised proofs — are identical to the reference's.
+//
+// Sharding: a key handle loaded with (shard_index, shard_count) keeps the
+// slice [len * i / cnt, len * (i+1) / cnt) of every list-valued field; the single points
+// live on shard 0.  prove then returns the shard's partial sums; the caller adds the
+// shards' partials (one tiny gather) to obtain the proof.
+#include <string.h>
+#include <algorithm>
+#include "fr_poly.cuh"
+#include "msm.cuh"
+#include "runtime.cuh"
+
+namespace zk {
+
+template <class T>
+struct Query {
+  BaseTable<T> table;
+  DevBuf<uint32_t> scalars;  // table.n canonical scalars
+  void load(const std::vector<uint8_t>& raw, uint32_t n, cudaStream_t st) {
+    bool pre = env_int("ZKB200_KEY_PRECOMPUTE", 1) != 0;
+    table.load(raw.data(), nullptr, n, pre, 0, st);
+    scalars.alloc((size_t)n * 8);
+  }
+};
+
+static void slice(size_t len, int idx, int cnt, uint32_t* lo, uint32_t* n) {
+  size_t a = len * (size_t)idx / cnt, b = len * (size_t)(idx + 1) / cnt;
+  *lo = (uint32_t)a;
+  *n = (uint32_t)(b - a);
+}
+static void append(std::vector<uint8_t>& dst, const uint8_t* src, size_t bytes) { dst.insert(dst.end(), src, src + bytes); }
+
+// ---- scalar helpers ------------------------------------------------------------------
+__device__ __forceinline__ void put_raw(uint32_t* dst, size_t i, const Fr& raw) { store_vec(reinterpret_cast<Fr*>(dst) + i, raw); }
+__device__ __forceinline__ Fr get_raw(const uint32_t* src, size_t i) { return load_vec_rw(reinterpret_cast<const Fr*>(src) + i); }
+__device__ __forceinline__ Fr raw_one() { Fr o = Fr::zero(); o.v[0] = 1; return o; }
+
+// ======================================================================================
+// Groth16
+// ======================================================================================
+struct G16Layout {
+  uint32_t n, ti_lo, ti_cnt, h_lo, h_cnt, mid_lo, mid_cnt;
+  int singles;  // 1 on the shard that owns a, b1, d1, b2, d2
+};
+
+struct Groth16Key : HandleBase {
+  G16Layout lay;
+  uint32_t m = 0, n_mid = 0;
+  Query<G1Traits> qC;       // [a, b1, d1 | ti1 | tiztd | ltd_mid]; A uses the prefix 3 + ti_cnt
+  Query<G2Traits> qB;       // [b2, d2 | ti2]
+  DevBuf<uint32_t> sA;      // scalars of A (prefix of the qC table)
+  DevBuf<uint32_t> mid_index;
+  DevBuf<uint32_t> d_sol, d_rs;
+  DevBuf<XYZZ<Fp>> r1;      // A, C
+  DevBuf<XYZZ<Fp2>> r2;     // B
+  DevBuf<uint8_t> d_out;
+  Groth16Key() { kind = 4; }
+};
+
+static __global__ void __launch_bounds__(128)
+k_groth16_scalars(G16Layout L, const Fr* __restrict__ vwy, const Fr* __restrict__ H,
+                  const uint32_t* __restrict__ sol_raw, const uint32_t* __restrict__ mid_index,
+                  const uint32_t* __restrict__ rs_raw, uint32_t* __restrict__ sA, uint32_t* __restrict__ sB,
+                  uint32_t* __restrict__ sC) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const Fr r_raw = get_raw(rs_raw, 0), s_raw = get_raw(rs_raw, 1);
+  if (t == 0) {
+    Fr zero = Fr::zero();
+    bool own = L.singles != 0;
+    Fr rs = (r_raw.to_mont() * s_raw.to_mont()).from_mont();
+    put_raw(sA, 0, own ? raw_one() : zero); put_raw(sA, 1, zero); put_raw(sA, 2, own ? r_raw : zero);
+    put_raw(sB, 0, own ? raw_one() : zero); put_raw(sB, 1, own ? s_raw : zero);
+    put_raw(sC, 0, own ? s_raw : zero); put_raw(sC, 1, own ? r_raw : zero); put_raw(sC, 2, own ? rs : zero);
+  }
+  if (t < L.ti_cnt) {
+    uint32_t i = L.ti_lo + t;
+    Fr v = load_vec_rw(&vwy[i]), w = load_vec_rw(&vwy[(size_t)L.n + i]);
+    put_raw(sA, 3 + t, v.from_mont());
+    put_raw(sB, 2 + t, w.from_mont());
+    Fr c = s_raw.to_mont() * v + r_raw.to_mont() * w;
+    put_raw(sC, 3 + t, c.from_mont());
+  }
+  if (t < L.h_cnt) put_raw(sC, 3 + (size_t)L.ti_cnt + t, load_vec_rw(&H[L.h_lo + t]).from_mont());
+  if (t < L.mid_cnt)
+    put_raw(sC, 3 + (size_t)L.ti_cnt + L.h_cnt + t, get_raw(sol_raw, mid_index[L.mid_lo + t]));
+}
+
+}  // namespace zk
+
+extern "C" {
+
+int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_count, uint64_t* handle) {
+  ZK_API_BEGIN
+  using namespace zk;
+  ZK_REQUIRE(pk && handle && pk->n >= 2 && pk->m >= 1 && shard_count >= 1 && shard_index >= 0 && shard_index < shard_count,
+             ZK_EARG, "groth16_pk_load: bad arguments");
+  ZK_REQUIRE(pk->a && pk->b1 && pk->d1 && pk->b2 && pk->d2 && pk->ti1 && pk->ti2 && pk->tiztd &&
+                 (pk->n_mid == 0 || (pk->ltd_mid && pk->mid_index)),
+             ZK_EARG, "groth16_pk_load: null key field");
+  for (size_t j = 0; j < pk->n_mid; j++) ZK_REQUIRE(pk->mid_index[j] < pk->m, ZK_EARG, "groth16_pk_load: mid_index out of range");
+  cudaStream_t st = default_stream();
+  auto k = std::make_unique<Groth16Key>();
+  G16Layout& L = k->lay;
+  L.n = (uint32_t)pk->n;
+  k->m = (uint32_t)pk->m;
+  k->n_mid = (uint32_t)pk->n_mid;
+  slice(pk->n, shard_index, shard_count, &L.ti_lo, &L.ti_cnt);
+  slice(pk->n - 1, shard_index, shard_count, &L.h_lo, &L.h_cnt);
+  slice(pk->n_mid, shard_index, shard_count, &L.mid_lo, &L.mid_cnt);
+  L.singles = shard_index == 0;
+  std::vector<uint8_t> t1, t2;
+  append(t1, pk->a, 96); append(t1, pk->b1, 96); append(t1, pk->d1, 96);
+  append(t1, pk->ti1 + (size_t)L.ti_lo * 96, (size_t)L.ti_cnt * 96);
+  append(t1, pk->tiztd + (size_t)L.h_lo * 96, (size_t)L.h_cnt * 96);
+  if (L.mid_cnt) append(t1, pk->ltd_mid + (size_t)L.mid_lo * 96, (size_t)L.mid_cnt * 96);
+  append(t2, pk->b2, 192); append(t2, pk->d2, 192);
+  append(t2, pk->ti2 + (size_t)L.ti_lo * 192, (size_t)L.ti_cnt * 192);
+  k->qC.load(t1, 3 + L.ti_cnt + L.h_cnt + L.mid_cnt, st);
+  k->qB.load(t2, 2 + L.ti_cnt, st);
+  k->sA.alloc((size_t)(3 + L.ti_cnt) * 8);
+  k->mid_index.alloc(pk->n_mid ? pk->n_mid : 1);
+  if (pk->n_mid) ZK_CUDA(cudaMemcpyAsync(k->mid_index.p, pk->mid_index, pk->n_mid * 4, cudaMemcpyHostToDevice, st));
+  k->d_sol.alloc((size_t)pk->m * 8);
+  k->d_rs.alloc(16);
+  k->r1.alloc(2);
+  k->r2.alloc(1);
+  k->d_out.alloc(ZK_GROTH16_PROOF_OUT);
+  ZK_CUDA(cudaStreamSynchronize(st));
+  *handle = register_handle(std::move(k));
+  ZK_API_END
+}
+
+static void groth16_finish(zk::Groth16Key* k, zk::QapDevice& q, cudaStream_t st, uint8_t* proof_out) {
+  using namespace zk;
+  const G16Layout& L = k->lay;
+  uint32_t span = std::max(std::max(L.ti_cnt, L.h_cnt), std::max(L.mid_cnt, 1u));
+  k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, q.Vc.p, q.H.p, k->d_sol.p, k->mid_index.p, k->d_rs.p, k->sA.p,
+                                                      k->qB.scalars.p, k->qC.scalars.p);
+  k->qC.table.run(k->sA.p, 3 + L.ti_cnt, k->r1.p + 0, st);             // A
+  k->qC.table.run(k->qC.scalars.p, k->qC.table.n, k->r1.p + 1, st);     // C
+  k->qB.table.run(k->qB.scalars.p, k->qB.table.n, k->r2.p, st);         // B
+  finalize_points<G1Traits>(k->r1.p + 0, 1, k->d_out.p, st);
+  finalize_points<G2Traits>(k->r2.p, 1, k->d_out.p + ZK_G1_OUT, st);
+  finalize_points<G1Traits>(k->r1.p + 1, 1, k->d_out.p + ZK_G1_OUT + ZK_G2_OUT, st);
+  int fl[2];
+  ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_GROTH16_PROOF_OUT, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "groth16_prove: scalar is not canonical (>= r)");
+  ZK_REQUIRE(fl[1] == 0, ZK_EREMAINDER, "groth16_prove: V*W - Y is not divisible by the target (QAP.ml:134)");
+}
+
+static void check_rs(const uint8_t* r, const uint8_t* s) {
+  // canonical check of the two blinding scalars on the host side of the ABI: byte compare with r
+  static const uint8_t R_LE[32] = {0x01, 0x00, 0x00, 0x00, 0xff, 0xff, 0xff, 0xff, 0xfe, 0x5b, 0xfe, 0xff, 0x02, 0xa4, 0xbd, 0x53,
+                                   0x05, 0xd8, 0xa1, 0x09, 0x08, 0xd8, 0x39, 0x33, 0x48, 0x7d, 0x9d, 0x29, 0x53, 0xa7, 0xed, 0x73};
+  for (const uint8_t* x : {r, s}) {
+    bool less = false;
+    for (int i = 31; i >= 0; i--) {
+      if (x[i] != R_LE[i]) { less = x[i] < R_LE[i]; break; }
+    }
+    ZK_REQUIRE(less, ZK_EPOINT, "blinding scalar is not canonical (>= r)");
+  }
+}
+
+int zk_groth16_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* sol, const uint8_t* r, const uint8_t* s,
+                     uint8_t* proof_out) {
+  ZK_API_BEGIN
+  using namespace zk;
+  auto* k = static_cast<Groth16Key*>(lookup_handle(pk_handle, 4));
+  auto* qh = static_cast<QapHandle*>(lookup_handle(qap_handle, 3));
+  QapDevice& q = qh->q;
+  ZK_REQUIRE(sol && r && s && proof_out, ZK_EARG, "groth16_prove: null argument");
+  ZK_REQUIRE(q.n == k->lay.n && q.m == k->m, ZK_EARG, "groth16_prove: key and QAP dimensions differ");
+  check_rs(r, s);
+  cudaStream_t st = default_stream();
+  ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
+  q.eval(k->d_sol.p, st);
+  groth16_finish(k, q, st, proof_out);
+  ZK_API_END
+}
+
+// Same, with V | W | Y given as coefficient vectors (3 * n scalars) instead of a dense QAP:
+// `qap_handle` then only carries the target (zk_qap_load with m = 0 ... see zk_quotient_domain_load).
+int zk_groth16_prove_coeffs(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* vwy, const uint8_t* sol,
+                            const uint8_t* r, const uint8_t* s, uint8_t* proof_out) {
+  ZK_API_BEGIN
+  using namespace zk;
+  auto* k = static_cast<Groth16Key*>(lookup_handle(pk_handle, 4));
+  auto* qh = static_cast<QapHandle*>(lookup_handle(qap_handle, 3));
+  QapDevice& q = qh->q;
+  ZK_REQUIRE(vwy && sol && r && s && proof_out, ZK_EARG, "groth16_prove_coeffs: null argument");
+  ZK_REQUIRE(q.n == k->lay.n, ZK_EARG, "groth16_prove_coeffs: key and domain dimensions differ");
+  check_rs(r, s);
+  cudaStream_t st = default_stream();
+  qh->d_raw.ensure(3 * (size_t)q.n * 8);
+  ZK_CUDA(cudaMemcpyAsync(qh->d_raw.p, vwy, 3 * (size_t)q.n * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
+  q.set_coeffs(qh->d_raw.p, st);
+  q.quotient_from_work(st);
+  groth16_finish(k, q, st, proof_out);
+  ZK_API_END
+}
+
+int zk_key_free(uint64_t handle) {
+  ZK_API_BEGIN
+  ZK_CUDA(cudaDeviceSynchronize());
+  zk::HandleBase* h = zk::lookup_handle(handle, 0);
+  ZK_REQUIRE(h->kind == 4 || h->kind == 5, ZK_EARG, "key_free: not a key handle");
+  zk::drop_handle(handle);
+  ZK_API_END
+}
+
+}  // extern "C"
+
+// ======================================================================================
+// Pinocchio (Protocol 2), NonZK and ZK
+// ======================================================================================
+namespace zk {
+
+struct PinLayout {
+  uint32_t n, m, mid_lo, mid_cnt, si_lo, si_cnt, all_lo, all_cnt;
+  int singles;
+};
+
+struct PinocchioKey : HandleBase {
+  PinLayout lay;
+  uint32_t m = 0, n_mid = 0;
+  // G1 queries: vv, yy, vavv, yayy, bvwy, h ; G2 queries: ww, waww
+  Query<G1Traits> q_vv, q_yy, q_vav, q_yay, q_bvwy, q_h;
+  Query<G2Traits> q_ww, q_waw;
+  DevBuf<uint32_t> mid_index, d_sol, d_d;
+  DevBuf<XYZZ<Fp>> r1;   // vv, yy, h, vavv, yayy, bvwy
+  DevBuf<XYZZ<Fp2>> r2;  // ww, waww
+  DevBuf<uint8_t> d_out;
+  PinocchioKey() { kind = 5; }
+};
+
+// Scalar vectors of the eight queries (pinocchio.ml:438-505):
+//   [dv | c_mid] for vv, vav ; [dw | c_mid] for ww, waw ; [dy | c_mid] for yy, yay ;
+//   [dv, dw, dy | c_mid] for bvwy ;
+//   h' : [-dy | h_i + dv dw target_i (si) | dw c (v_all) | dv c (w_all)]
+static __global__ void __launch_bounds__(128)
+k_pinocchio_scalars(PinLayout L, const Fr* __restrict__ H, const Fr* __restrict__ target,
+                    const uint32_t* __restrict__ sol_raw, const uint32_t* __restrict__ mid_index,
+                    const uint32_t* __restrict__ d_raw, uint32_t* s_vv, uint32_t* s_ww, uint32_t* s_yy, uint32_t* s_vav,
+                    uint32_t* s_waw, uint32_t* s_yay, uint32_t* s_bvwy, uint32_t* s_h) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const Fr dv = get_raw(d_raw, 0), dw = get_raw(d_raw, 1), dy = get_raw(d_raw, 2);
+  const Fr zero = Fr::zero();
+  const bool own = L.singles != 0;
+  if (t == 0) {
+    put_raw(s_vv, 0, own ? dv : zero); put_raw(s_vav, 0, own ? dv : zero);
+    put_raw(s_ww, 0, own ? dw : zero); put_raw(s_waw, 0, own ? dw : zero);
+    put_raw(s_yy, 0, own ? dy : zero); put_raw(s_yay, 0, own ? dy : zero);
+    put_raw(s_bvwy, 0, own ? dv : zero); put_raw(s_bvwy, 1, own ? dw : zero); put_raw(s_bvwy, 2, own ? dy : zero);
+    put_raw(s_h, 0, own ? dy.to_mont().neg().from_mont() : zero);
+  }
+  if (t < L.mid_cnt) {
+    Fr c = get_raw(sol_raw, mid_index[L.mid_lo + t]);
+    put_raw(s_vv, 1 + t, c); put_raw(s_vav, 1 + t, c); put_raw(s_ww, 1 + t, c); put_raw(s_waw, 1 + t, c);
+    put_raw(s_yy, 1 + t, c); put_raw(s_yay, 1 + t, c); put_raw(s_bvwy, 3 + t, c);
+  }
+  if (t < L.si_cnt) {
+    uint32_t i = L.si_lo + t;
+    Fr hv = (i + 1 < L.n) ? load_vec_rw(&H[i]) : zero;                 // h has n - 1 coefficients
+    Fr dvdw = dv.to_mont() * dw.to_mont();
+    Fr tv = load_vec_rw(&target[i]);                                    // n + 1 coefficients
+    put_raw(s_h, 1 + t, (hv + dvdw * tv).from_mont());
+  }
+  if (t < L.all_cnt) {
+    Fr c = get_raw(sol_raw, L.all_lo + t).to_mont();
+    put_raw(s_h, 1 + (size_t)L.si_cnt + t, (dw.to_mont() * c).from_mont());
+    put_raw(s_h, 1 + (size_t)L.si_cnt + L.all_cnt + t, (dv.to_mont() * c).from_mont());
+  }
+}
+
+}  // namespace zk
+
+extern "C" {
+
+int zk_pinocchio_pk_load(const zk_pinocchio_pkey* pk, int shard_index, int shard_count, uint64_t* handle) {
+  ZK_API_BEGIN
+  using namespace zk;
+  ZK_REQUIRE(pk && handle && pk->n >= 2 && pk->m >= 1 && shard_count >= 1 && shard_index >= 0 && shard_index < shard_count,
+             ZK_EARG, "pinocchio_pk_load: bad arguments");
+  ZK_REQUIRE(pk->si && pk->v_all && pk->w_all && pk->one && pk->vt && pk->wt && pk->yt && pk->vavt && pk->wawt &&
+                 pk->yayt && pk->vbt && pk->wbt && pk->ybt &&
+                 (pk->n_mid == 0 || (pk->vv && pk->ww && pk->yy && pk->vav && pk->waw && pk->yay && pk->bvwy && pk->mid_index)),
+             ZK_EARG, "pinocchio_pk_load: null key field");
+  for (size_t j = 0; j < pk->n_mid; j++) ZK_REQUIRE(pk->mid_index[j] < pk->m, ZK_EARG, "pinocchio_pk_load: mid_index out of range");
+  cudaStream_t st = default_stream();
+  auto k = std::make_unique<PinocchioKey>();
+  PinLayout& L = k->lay;
+  L.n = (uint32_t)pk->n;
+  L.m = (uint32_t)pk->m;
+  k->m = L.m;
+  k->n_mid = (uint32_t)pk->n_mid;
+  slice(pk->n_mid, shard_index, shard_count, &L.mid_lo, &L.mid_cnt);
+  slice(pk->n + 1, shard_index, shard_count, &L.si_lo, &L.si_cnt);
+  slice(pk->m, shard_index, shard_count, &L.all_lo, &L.all_cnt);
+  L.singles = shard_index == 0;
+  auto g1q = [&](Query<G1Traits>& q, std::initializer_list<const uint8_t*> singles, const uint8_t* list) {
+    std::vector<uint8_t> raw;
+    for (const uint8_t* sp : singles) append(raw, sp, 96);
+    if (L.mid_cnt) append(raw, list + (size_t)L.mid_lo * 96, (size_t)L.mid_cnt * 96);
+    q.load(raw, (uint32_t)singles.size() + L.mid_cnt, st);
+  };
+  auto g2q = [&](Query<G2Traits>& q, const uint8_t* single, const uint8_t* list) {
+    std::vector<uint8_t> raw;
+    append(raw, single, 192);
+    if (L.mid_cnt) append(raw, list + (size_t)L.mid_lo * 192, (size_t)L.mid_cnt * 192);
+    q.load(raw, 1 + L.mid_cnt, st);
+  };
+  g1q(k->q_vv, {pk->vt}, pk->vv);
+  g1q(k->q_yy, {pk->yt}, pk->yy);
+  g1q(k->q_vav, {pk->vavt}, pk->vav);
+  g1q(k->q_yay, {pk->yayt}, pk->yay);
+  g1q(k->q_bvwy, {pk->vbt, pk->wbt, pk->ybt}, pk->bvwy);
+  g2q(k->q_ww, pk->wt, pk->ww);
+  g2q(k->q_waw, pk->wawt, pk->waw);
+  {
+    std::vector<uint8_t> raw;
+    append(raw, pk->one, 96);
+    append(raw, pk->si + (size_t)L.si_lo * 96, (size_t)L.si_cnt * 96);
+    append(raw, pk->v_all + (size_t)L.all_lo * 96, (size_t)L.all_cnt * 96);
+    append(raw, pk->w_all + (size_t)L.all_lo * 96, (size_t)L.all_cnt * 96);
+    k->q_h.load(raw, 1 + L.si_cnt + 2 * L.all_cnt, st);
+  }
+  k->mid_index.alloc(pk->n_mid ? pk->n_mid : 1);
+  if (pk->n_mid) ZK_CUDA(cudaMemcpyAsync(k->mid_index.p, pk->mid_index, pk->n_mid * 4, cudaMemcpyHostToDevice, st));
+  k->d_sol.alloc((size_t)pk->m * 8);
+  k->d_d.alloc(24);
+  k->r1.alloc(6);
+  k->r2.alloc(2);
+  k->d_out.alloc(ZK_PINOCCHIO_PROOF_OUT);
+  ZK_CUDA(cudaStreamSynchronize(st));
+  *handle = register_handle(std::move(k));
+  ZK_API_END
+}
+
+// d: three blinding scalars dv | dw | dy (ZK.prove), or NULL for NonZK.prove.
+// proof_out: vv | ww | yy | h | vavv | waww | yayy | bvwy as point results (pinocchio.ml:195-208 order).
+int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* sol, const uint8_t* d, uint8_t* proof_out) {
+  ZK_API_BEGIN
+  using namespace zk;
+  auto* k = static_cast<PinocchioKey*>(lookup_handle(pk_handle, 5));
+  auto* qh = static_cast<QapHandle*>(lookup_handle(qap_handle, 3));
+  QapDevice& q = qh->q;
+  ZK_REQUIRE(sol && proof_out, ZK_EARG, "pinocchio_prove: null argument");
+  ZK_REQUIRE(q.n == k->lay.n && q.m == k->m, ZK_EARG, "pinocchio_prove: key and QAP dimensions differ");
+  uint8_t zeros[96] = {0};
+  const uint8_t* dd = d ? d : zeros;
+  if (d) { check_rs(d, d + 32); check_rs(d + 64, d + 64); }
+  cudaStream_t st = default_stream();
+  const PinLayout& L = k->lay;
+  ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(k->d_d.p, dd, 96, cudaMemcpyHostToDevice, st));
+  q.eval(k->d_sol.p, st);
+  uint32_t span = std::max(std::max(L.mid_cnt, L.si_cnt), std::max(L.all_cnt, 1u));
+  k_pinocchio_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, q.H.p, q.target.p, k->d_sol.p, k->mid_index.p, k->d_d.p,
+                                                        k->q_vv.scalars.p, k->q_ww.scalars.p, k->q_yy.scalars.p,
+                                                        k->q_vav.scalars.p, k->q_waw.scalars.p, k->q_yay.scalars.p,
+                                                        k->q_bvwy.scalars.p, k->q_h.scalars.p);
+  auto run1 = [&](Query<G1Traits>& qq, int slot) { qq.table.run(qq.scalars.p, qq.table.n, k->r1.p + slot, st); };
+  auto run2 = [&](Query<G2Traits>& qq, int slot) { qq.table.run(qq.scalars.p, qq.table.n, k->r2.p + slot, st); };
+  run1(k->q_vv, 0); run1(k->q_yy, 1); run1(k->q_h, 2); run1(k->q_vav, 3); run1(k->q_yay, 4); run1(k->q_bvwy, 5);
+  run2(k->q_ww, 0); run2(k->q_waw, 1);
+  // output order: vv ww yy h vavv waww yayy bvwy
+  uint8_t* o = k->d_out.p;
+  finalize_points<G1Traits>(k->r1.p + 0, 1, o, st); o += ZK_G1_OUT;
+  finalize_points<G2Traits>(k->r2.p + 0, 1, o, st); o += ZK_G2_OUT;
+  finalize_points<G1Traits>(k->r1.p + 1, 1, o, st); o += ZK_G1_OUT;
+  finalize_points<G1Traits>(k->r1.p + 2, 1, o, st); o += ZK_G1_OUT;
+  finalize_points<G1Traits>(k->r1.p + 3, 1, o, st); o += ZK_G1_OUT;
+  finalize_points<G2Traits>(k->r2.p + 1, 1, o, st); o += ZK_G2_OUT;
+  finalize_points<G1Traits>(k->r1.p + 4, 1, o, st); o += ZK_G1_OUT;
+  finalize_points<G1Traits>(k->r1.p + 5, 1, o, st);
+  int fl[2];
+  ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_PINOCCHIO_PROOF_OUT, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "pinocchio_prove: scalar is not canonical (>= r)");
+  ZK_REQUIRE(fl[1] == 0, ZK_EREMAINDER, "pinocchio_prove: V*W - Y is not divisible by the target (QAP.ml:134)");
+  ZK_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+"""Host mirror of ``Curve.Bls12_381`` (/root/reference/src/lib/zk/curve.ml:74-221).
+
+``Fr`` values are Python ints mod r (host-side scalar bookkeeping, as in the OCaml
+host).  ``G1`` / ``G2`` values are opaque byte-backed points (the counterpart of the
+reference's custom blocks) and EVERY group operation — ``+``, ``*``, ``~-``, ``sum``,
+``dot``, ``apply_powers``, ``powers``, ``of_Fr`` — is executed by the CUDA library
+through the C ABI (``zk_g*_msm`` / ``zk_g*_fixed_base_mul``).  ``README.md:36-40`` of
+the reference spells the module ``Ecp``; ``Ecp = Curve`` aliases are provided in
+``zukelang_b200/__init__``-level imports for both spellings.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import random
+from typing import Callable, Dict, Iterable, List, Sequence, Tuple
+
+from . import _lib
+
+Var = Tuple[str, int]
+
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+class Fr:
+    """curve.ml:121-155.  Elements are ints in [0, r)."""
+    order = R
+    zero = 0
+    one = 1
+
+    @staticmethod
+    def of_int(i: int) -> int:
+        return i % R
+
+    of_z = of_int
+
+    @staticmethod
+    def add(a, b): return (a + b) % R
+    @staticmethod
+    def sub(a, b): return (a - b) % R
+    @staticmethod
+    def mul(a, b): return (a * b) % R
+    @staticmethod
+    def neg(a): return (-a) % R
+
+    @staticmethod
+    def div(a, b):
+        if b % R == 0:
+            raise ZeroDivisionError("Fr division by zero")
+        return a * pow(b, -1, R) % R
+
+    @staticmethod
+    def pow(a, e: int): return pow(a, e, R)
+
+    @staticmethod
+    def gen(rng: random.Random) -> int:
+        """curve.ml:136 ``Fr.random ~state:rng ()``."""
+        return rng.randrange(R)
+
+    @staticmethod
+    def to_bytes(a: int) -> bytes:
+        return (a % R).to_bytes(32, "little")
+
+    @staticmethod
+    def of_bytes(b: bytes) -> int:
+        v = int.from_bytes(b, "little")
+        if v >= R:
+            raise ValueError("Fr.of_bytes: not canonical")
+        return v
+
+
+def fr_vector(ks: Iterable[int]) -> bytes:
+    return b"".join((k % R).to_bytes(32, "little") for k in ks)
+
+
+class Point:
+    """An opaque group element: uncompressed wire bytes (+ lazily the compressed form)."""
+    __slots__ = ("raw", "_comp")
+
+    def __init__(self, raw: bytes, comp: bytes | None = None):
+        self.raw = bytes(raw)
+        self._comp = comp
+
+    def __eq__(self, other):
+        return isinstance(other, Point) and self.raw == other.raw
+
+    def __hash__(self):
+        return hash(self.raw)
+
+    def __repr__(self):
+        return "Point(%s…)" % self.raw[:8].hex()
+
+    def is_zero(self) -> bool:
+        return self.raw[0] == 0x40
+
+
+class _Group:
+    """The ``G`` signature of curve.ml:22-50 for one group, backed by the CUDA library."""
+
+    def __init__(self, name: str, raw: int, comp: int, gen_raw_hex: str):
+        self.name, self.RAW, self.COMP, self.OUT = name, raw, comp, raw + comp
+        self._msm = "zk_%s_msm" % name.lower()
+        self._fixed = "zk_%s_fixed_base_mul" % name.lower()
+        self.zero = Point(bytes([0x40]) + bytes(raw - 1))
+        self.one = Point(bytes.fromhex(gen_raw_hex))
+
+    # ---- the MSM primitive everything else reduces to ------------------------------
+    def msm(self, points: Sequence[Point], scalars: Sequence[int]) -> Point:
+        """sum_i scalars[i] * points[i]   (curve.ml:91-103 as one call)."""
+        if len(points) != len(scalars):
+            raise _lib.InvalidArgument(_lib.ZK_EARG, "msm: length mismatch")
+        out = (ctypes.c_uint8 * self.OUT)()
+        n = len(points)
+        if n == 0:
+            return self.zero
+        bases = b"".join(p.raw for p in points)
+        _lib.check(getattr(_lib.lib(), self._msm)(bases, None, fr_vector(scalars), n, out))
+        b = bytes(out)
+        return Point(b[:self.RAW], b[self.RAW:])
+
+    # ---- curve.ml:159-191 ExtendG -----------------------------------------------------
+    def add(self, a: Point, b: Point) -> Point:
+        return self.msm([a, b], [1, 1])
+
+    def mul(self, a: Point, k: int) -> Point:
+        return self.msm([a], [k % R])
+
+    def neg(self, a: Point) -> Point:
+        return self.msm([a], [R - 1])
+
+    def sub(self, a: Point, b: Point) -> Point:
+        return self.msm([a, b], [1, R - 1])
+
+    def eq(self, a: Point, b: Point) -> bool:
+        return a.raw == b.raw
+
+    def sum(self, pts: Sequence[Point]) -> Point:
+        return self.msm(list(pts), [1] * len(pts))
+
+    def of_Fr(self, k: int) -> Point:                      # curve.ml:180
+        return self.fixed_base([k])[0]
+
+    def fixed_base(self, ks: Sequence[int]) -> List[Point]:
+        n = len(ks)
+        if n == 0:
+            return []
+        out = (ctypes.c_uint8 * (self.RAW * n))()
+        _lib.check(getattr(_lib.lib(), self._fixed)(fr_vector(ks), n, out))
+        b = bytes(out)
+        return [Point(b[i * self.RAW:(i + 1) * self.RAW]) for i in range(n)]
+
+    # ---- curve.ml:79-119 ExtendMap ------------------------------------------------------
+    def sum_map(self, m: Dict[Var, object], f: Callable[[Var, object], Point]) -> Point:
+        """curve.ml:91."""
+        return self.sum([f(k, m[k]) for k in sorted(m)])
+
+    def dot(self, m: Dict[Var, Point], c: Dict[Var, int]) -> Point:
+        """curve.ml:94-103; a domain mismatch is ``assert false`` in the reference."""
+        if set(m) != set(c):
+            raise AssertionError("Domain mismatch")
+        keys = sorted(m)
+        return self.msm([m[k] for k in keys], [c[k] for k in keys])
+
+    def powers(self, d: int, s: int) -> List[Point]:
+        """curve.ml:106-109 — d + 1 points g^(s^i)."""
+        ks, cur = [], 1
+        for _ in range(d + 1):
+            ks.append(cur)
+            cur = cur * s % R
+        return self.fixed_base(ks)
+
+    def apply_powers(self, cs: Sequence[int], xis: Sequence[Point]) -> Point:
+        """curve.ml:112-118 — Invalid_argument "apply_powers" when cs is longer than xis."""
+        if len(cs) > len(xis):
+            raise _lib.InvalidArgument(_lib.ZK_EARG, "apply_powers")
+        return self.msm(list(xis[:len(cs)]), list(cs))
+
+    def to_compressed_bytes(self, a: Point) -> bytes:
+        """curve.ml:199 / :208."""
+        if a._comp is None:
+            a._comp = self.msm([a], [1])._comp
+        return a._comp
+
+    def to_bytes(self, a: Point) -> bytes:
+        return a.raw
+
+
+_G1_GEN = ("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+           "08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1")
+_G2_GEN = ("13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+           "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8"
+           "0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be"
+           "0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801")
+
+
+class Bls12_381:
+    """``Curve.Bls12_381`` (curve.mli:56-60).  GT / Pairing belong to the verifier and are
+    outside the accelerated path."""
+    Fr = Fr
+    G1 = _Group("G1", 96, 48, _G1_GEN)
+    G2 = _Group("G2", 192, 96, _G2_GEN)
