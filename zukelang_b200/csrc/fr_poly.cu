@@ -56,7 +56,7 @@ static __global__ void k_ntt_consts(int logD, Fr* consts) {
   Fr w, wi, g, gi, i2;
   for (int i = 0; i < 8; i++) {
     w.v[i] = FrParams::root32(i); wi.v[i] = FrParams::root32_inv(i);
-    g.v[i] = FrParams::gen7(i); gi.v[i] = FrParams::gen7_inv(i); i2.v[i] = FrParams::inv2(i);
+    g.v[i] = FrParams::coset_g(i); gi.v[i] = FrParams::coset_g_inv(i); i2.v[i] = FrParams::inv2(i);
   }
   for (int i = logD; i < 32; i++) { w = w * w; wi = wi * wi; }
   Fr dinv = Fr::one();
