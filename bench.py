@@ -1,0 +1,395 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200 prover hot path.
+
+Metric (BASELINE.json): BLS12-381 G1 MSM throughput, Mpts/s, at 2^20 points.
+A "step" is ONE multi-scalar multiplication of 2^20 uniformly random Fr scalars against a
+resident proving-key-style base table (scalars from PCG64(0x5A554B45),
+bases P_i = d_i * G with known discrete logs so the result is checked exactly every run).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N = 1: one process.  N > 1: launched by torchrun, one rank per GPU; the 2^20 points are
+sharded by base range across ranks ("strong" scaling), each rank reduces its
+shard, the N partial sums (96 B each) are all-gathered over NCCL and summed on every rank.
+
+Fields beyond the base contract:
+  roofline      dominant kernel (k_accumulate) against the integer-multiply pipe: algorithmic
+                MAC32 per launch (48 000 per point) / CUDA-event duration of that
+                kernel in the timed steps / the IMAD-chain peak measured in this same process.
+  cpu_baseline  the oracle's C restatement of the reference's fold-MSM on the host cores
+                (bounded sample), rank 0 / N = 1 only.
+  e2e           same metric through the host-buffer C-ABI call (pinned host scalars in, point out).
+--impl reference runs only the CPU restatement (the reference itself needs OCaml, absent here).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+MAC32_PER_POINT = 48_000          # 16 windows x 3 000 MAC32 (G1 XYZZ mixed add)
+LOG_N = 20
+SEED_SCALARS, SEED_BASES = 0x5A554B45, 0x42415345
+
+
+def words_to_ints(w):
+    return [int(a) | (int(b) << 64) | (int(c) << 128) | (int(d) << 192) for a, b, c, d in w]
+
+
+def uniform_scalars(n, seed):
+    """n scalars uniform in [0, r): four u64 words from PCG64(seed), reduced mod r.
+    Returns (uint64 array (n, 4) little-endian words, list of python ints)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    ints = [v % R for v in words_to_ints(w.tolist())]
+    out = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in ints), dtype=np.uint64).reshape(n, 4).copy()
+    return out, ints
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.rows, self.proc, self.idx = [], None, device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        # "under load": keep the upper half of the samples (idle samples before/after sit at the bottom)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ------------------------------------------------------------------------------------------
+def load_c_oracle():
+    so = os.path.join(ROOT, "oracle", "c", "libzkoracle.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(so)
+    lib.zkoracle_g1_msm_fold.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    lib.zkoracle_g1_msm_fold.restype = ctypes.c_int
+    return lib
+
+
+def cpu_fold_msm(bases_raw, scalars_raw, n, threads):
+    """The oracle's restatement of curve.ml:91-118 on `threads` host cores; returns (seconds, out96)."""
+    lib = load_c_oracle()
+    out = (ctypes.c_uint8 * 96)()
+    t0 = time.perf_counter()
+    lib.zkoracle_g1_msm_fold(bases_raw, scalars_raw, n, threads, out)
+    return time.perf_counter() - t0, bytes(out)
+
+
+def oracle_bases(n, seed):
+    """n bases d_i * G on the CPU (python oracle, small n only) -> raw bytes, dlogs."""
+    from oracle import bls12_381 as O
+    import random
+    rng = random.Random(seed)
+    dl = [rng.randrange(1, 1 << 40) for _ in range(n)]
+    # one running addition chain keeps this O(n) group operations
+    step = O.G1.mul(O.G1.one, 1 << 20)
+    pts, cur, acc_d = [], O.G1.mul(O.G1.one, dl[0]), dl[0]
+    dl_out = []
+    for i in range(n):
+        pts.append(cur)
+        dl_out.append(acc_d)
+        cur = O.G1.add(cur, step)
+        acc_d += 1 << 20
+    return b"".join(O.g1_to_uncompressed(p) for p in pts), dl_out
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own algorithm on the host cores (oracle port; the OCaml
+    reference cannot be built in this image)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    threads = os.cpu_count() or 1
+    sample = 1 << 12                              # bounded sample of the 2^20 workload per step
+    bases_raw, dl = oracle_bases(sample, SEED_BASES)
+    _, ints = uniform_scalars(sample, SEED_SCALARS)
+    sc_raw = b"".join(v.to_bytes(32, "little") for v in ints)
+    from oracle import bls12_381 as O
+    expect = O.g1_to_uncompressed(O.G1.mul(O.G1.one, sum(a * b for a, b in zip(ints, dl)) % R))
+    times = []
+    for it in range(args.warmup + args.steps):
+        dt, out = cpu_fold_msm(bases_raw, sc_raw, sample, threads)
+        assert out == expect, "CPU restatement disagrees with the closed form"
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = sample * len(times) / total / 1e6
+    line = {"impl": "reference", "metric": "bls12_381_g1_msm_throughput", "value": val, "unit": "Mpts/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32-limb modular (Fp 381-bit)",
+            "data": "synthetic", "config": {"workload": "G1 MSM, 2^20 points, uniform 255-bit scalars (config 4)",
+                                            "sample": "first 2^12 points per step", "algorithm": "reference fold of double-and-add scalar muls (curve.ml:91-118)"},
+            "cpu_baseline": {"value": val, "unit": "Mpts/s", "cores": threads, "kind": "port",
+                             "sample": "2^12 of the 2^20 points per step, oracle/c fold-MSM on all host threads"},
+            "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    from zukelang_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("ZKB200_DEVICE", str(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    zk = _lib.lib()
+    n_total = 1 << args.logn
+    lo, hi = n_total * rank // world, n_total * (rank + 1) // world
+    n = hi - lo
+
+    # ---- setup (untimed): bases with known discrete logs, resident precomputed table ----------
+    t0 = time.time()
+    dl_w_all, dl_all = uniform_scalars(n_total, SEED_BASES)
+    dl_w = np.ascontiguousarray(dl_w_all[lo:hi])
+    bases = np.empty(n * 96, dtype=np.uint8)
+    _lib.check(zk.zk_g1_fixed_base_mul(dl_w.ctypes.data, n, bases.ctypes.data))
+    handle = ctypes.c_uint64()
+    _lib.check(zk.zk_g1_table_load(bases.ctypes.data, None, n, 1, args.window_bits, ctypes.byref(handle)))
+    info = (ctypes.c_uint64 * 8)()
+    _lib.check(zk.zk_table_info(handle.value, info))
+    setup_s = time.time() - t0
+
+    # scalar batches: distinct per step (rotating pool), resident in HBM for `value`,
+    # in pinned host memory for `e2e`
+    pool = min(4, args.steps + args.warmup)
+    batches = []
+    for b in range(pool):
+        w, ints = uniform_scalars(n_total, SEED_SCALARS + b)
+        tot = sum(a * d for a, d in zip(ints, dl_all)) % R
+        host = torch.from_numpy(np.ascontiguousarray(w[lo:hi]).view(np.int64)).pin_memory()
+        batches.append({"host": host, "dev": host.cuda(), "expect_dlog": tot})
+    d_out = torch.zeros(144, dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    gathered = torch.zeros(world * 96, dtype=torch.uint8, device="cuda")
+    d_sum = torch.zeros(144, dtype=torch.uint8, device="cuda")
+
+    def reduce_shards():
+        """N > 1: all-gather the 96-byte partial sums over NCCL and add them on every rank"""
+        dist.all_gather_into_tensor(gathered, d_out[:96].contiguous())
+        _lib.check(zk.zk_g1_sum_dev(gathered.data_ptr(), world, d_sum.data_ptr(), side.cuda_stream))
+        return d_sum
+
+    def step_device(b):
+        """one MSM with device-resident scalars; returns the result tensor (on device)"""
+        _lib.check(zk.zk_g1_table_msm_dev(handle.value, batches[b]["dev"].data_ptr(), n, d_out.data_ptr(), side.cuda_stream))
+        return d_out if world == 1 else reduce_shards()
+
+    def combine(res):
+        return bytes(res.cpu().numpy())[:96]
+
+    def expected_point(tot):
+        exp = np.empty(96, dtype=np.uint8)
+        _lib.check(zk.zk_g1_fixed_base_mul(tot.to_bytes(32, "little"), 1, exp.ctypes.data))
+        return bytes(exp)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- integer-pipe peak, measured in this process (denominator of the roofline) -------------
+    ops, ms = ctypes.c_double(), ctypes.c_double()
+    peak_imad = 0.0
+    for _ in range(3):
+        _lib.check(zk.zk_bench_intpipe(1, 4096, ctypes.byref(ops), ctypes.byref(ms)))
+        peak_imad = max(peak_imad, ops.value)
+    peak_mac32 = peak_imad / 2.0                       # one MAC32 = mad.lo + mad.hi
+
+    # ---- warm-up, with the exact known-dlog check -------------------------------------------
+    with torch.cuda.stream(side):
+        for it in range(args.warmup):
+            b = it % pool
+            parts = step_device(b)
+            side.synchronize()
+            got = combine(parts)
+            assert got == expected_point(batches[b]["expect_dlog"]), "MSM result differs from the known-dlog closed form"
+
+    # ---- timed region: `value` (inputs resident in HBM) -----------------------------------------
+    _lib.check(zk.zk_table_profile(handle.value, 1, None))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    acc_ms, stage = [], (ctypes.c_float * 4)()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(side):
+        e0.record(side)
+        for it in range(args.steps):
+            parts = step_device((args.warmup + it) % pool)
+        e1.record(side)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    _lib.check(zk.zk_table_profile(handle.value, 1, stage))     # stages of the last timed step
+    acc_last_ms = float(stage[1])
+    stages_last = [float(x) for x in stage]
+    clocks = sampler.stop()
+    final = combine(parts)
+    assert final == expected_point(batches[(args.warmup + args.steps - 1) % pool]["expect_dlog"])
+    # per-step accumulate time over a few more profiled steps (events are per step)
+    with torch.cuda.stream(side):
+        for it in range(min(args.steps, 5)):
+            step_device(it % pool)
+            side.synchronize()
+            _lib.check(zk.zk_table_profile(handle.value, 1, stage))
+            acc_ms.append(float(stage[1]))
+    _lib.check(zk.zk_table_profile(handle.value, 0, None))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = n_total * args.steps / (dev_ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers through the public C-ABI call (H2D + MSM + D2H per step) ---------------
+    out_host = torch.zeros(144, dtype=torch.uint8).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(side):
+        for it in range(args.steps):
+            b = (args.warmup + it) % pool
+            _lib.check(zk.zk_g1_table_msm(handle.value, batches[b]["host"].data_ptr(), n, out_host.data_ptr()))
+            if world > 1:
+                d_out.copy_(out_host, non_blocking=True)
+                res = reduce_shards()
+                out_host.copy_(res)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_val = n_total * args.steps / e2e_s / 1e6
+
+    if rank == 0:
+        c, W = int(info[0]), int(info[1])
+        acc_avg = sum(acc_ms) / len(acc_ms)
+        achieved = n * MAC32_PER_POINT / (acc_avg * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        algo_bytes = n * (W * 96 + 32)                                   # gathered bases + scalars
+        line = {
+            "metric": "bls12_381_g1_msm_throughput", "value": value, "unit": "Mpts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32-limb modular (Fp 381-bit, Fr 255-bit)",
+            "data": "synthetic",
+            "config": {"workload": "G1 MSM, 2^%d points, uniform 255-bit scalars (BASELINE configs[3], SURVEY §8d config 4)" % args.logn,
+                       "points": n_total, "points_per_gpu": n, "window_bits": c, "windows": W,
+                       "precomputed_table": bool(info[7]), "table_MiB_per_gpu": int(info[5]) >> 20,
+                       "segments": int(info[4]), "true_mixed_adds_per_point": W,
+                       "l2": "inputs larger than L2 (table %d MiB, %d rotating scalar batches of %d MiB)" % (int(info[5]) >> 20, pool, (n * 32) >> 20),
+                       "parallelism": "base-range shards x%d, all_gather of 96-B partial sums" % world, "setup_s": setup_s},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 144,
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": (10 if world == 1 else 12) * args.steps,
+            "roofline": {"bound": "int32-imad", "kernel": "k_accumulate<Fp>", "achieved": achieved,
+                         "peak": peak_mac32 / 1e12, "unit": "TMAC32/s", "frac": achieved / (peak_mac32 / 1e12),
+                         "traffic": None, "kernel_ms": acc_avg, "stages_ms_last_step": stages_last,
+                         "algorithmic_mac32_per_point": MAC32_PER_POINT,
+                         "peak_source": "mad.lo.cc/madc.hi.cc chains measured in this process (zk_bench_intpipe), /2",
+                         "whole_step_frac": n_total / world * MAC32_PER_POINT / (dev_ms / args.steps * 1e-3) / peak_mac32,
+                         "hbm": {"achieved_gbs": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                 "frac": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sample = 1 << 14
+            sc_raw = batches[0]["host"].numpy().tobytes()[:sample * 32]
+            secs, out = cpu_fold_msm(bases[:sample * 96].tobytes(), sc_raw, sample, threads)
+            line["cpu_baseline"] = {"value": sample / secs / 1e6, "unit": "Mpts/s", "cores": threads, "kind": "port",
+                                    "sample": "first 2^14 of the 2^20 points, oracle/c fold of double-and-add scalar muls "
+                                              "(curve.ml:91-118) on all host threads, %.1f s" % secs}
+        print(json.dumps(line), flush=True)
+    _lib.check(zk.zk_table_free(handle.value))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--logn", type=int, default=LOG_N)
+    ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,7 +80,20 @@ int zk_g2_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *
 /* info[0] = window bits c, [1] = windows W, [2] = bucket windows, [3] = buckets per window,
  * [4] = segments, [5] = device bytes, [6] = points, [7] = precomputed */
 int zk_table_info(uint64_t handle, uint64_t info[8]);
+/* Stage timing for the roofline leg of bench.py: enable != 0 makes the following MSMs on this
+ * table bracket their stages with CUDA events on the launching stream; stage_ms (nullable)
+ * receives the last profiled run's times once that stream has been synchronised:
+ * [0] digits + scan + scatter, [1] bucket accumulation, [2] bucket reduction, [3] window combine. */
+int zk_table_profile(uint64_t handle, int enable, float stage_ms[4]);
 int zk_table_free(uint64_t handle);
+
+/* ---- sum of k points (combining the shards' partial results) ------
+ * points: k uncompressed points; out: a point result.  Replaces G.sum / repeated G.( + )
+ * (curve.ml:163,178).  The _dev form takes device pointers and enqueues on cuda_stream. */
+int zk_g1_sum(const uint8_t *points, size_t k, uint8_t out[ZK_G1_OUT]);
+int zk_g2_sum(const uint8_t *points, size_t k, uint8_t out[ZK_G2_OUT]);
+int zk_g1_sum_dev(const void *d_points, size_t k, void *d_out, void *cuda_stream);
+int zk_g2_sum_dev(const void *d_points, size_t k, void *d_out, void *cuda_stream);
 
 /* ---- fixed-base batch: out[i] = scalars[i] * generator -------------------------
  * Replaces Curve.G.of_Fr (curve.ml:180) / powers (:106-109) when applied to a vector.

@@ -45,7 +45,12 @@ SIGNATURES = {
     "zk_g1_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_g2_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_table_info": (c_int, [c_uint64, POINTER(c_uint64)]),
+    "zk_table_profile": (c_int, [c_uint64, c_int, c_void_p]),
     "zk_table_free": (c_int, [c_uint64]),
+    "zk_g1_sum": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "zk_g2_sum": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "zk_g1_sum_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "zk_g2_sum_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_g1_fixed_base_mul": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_g2_fixed_base_mul": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_qap_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, POINTER(c_uint64)]),

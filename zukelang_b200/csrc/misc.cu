@@ -173,6 +173,23 @@ int zk_test_field_op(int field, int op, const uint32_t* a, const uint32_t* b, ui
   ZK_API_END
 }
 
+int zk_table_profile(uint64_t handle, int enable, float stage_ms[4]) {
+  ZK_API_BEGIN
+  using namespace zk;
+  HandleBase* hb = lookup_handle(handle, 0);
+  ZK_REQUIRE(hb->kind == 1 || hb->kind == 2, ZK_EARG, "table_profile: not a table handle");
+  if (hb->kind == 1) {
+    auto* h = static_cast<TableHandle<G1Traits>*>(hb);
+    if (stage_ms) h->table.stage_ms(stage_ms);
+    h->table.profile = enable != 0;
+  } else {
+    auto* h = static_cast<TableHandle<G2Traits>*>(hb);
+    if (stage_ms) h->table.stage_ms(stage_ms);
+    h->table.profile = enable != 0;
+  }
+  ZK_API_END
+}
+
 int zk_table_info(uint64_t handle, uint64_t info[8]) {
   ZK_API_BEGIN
   using namespace zk;

@@ -376,6 +376,13 @@ struct BaseTable {
   void build_tables(cudaStream_t st);
   // d_scalars: count * 32 B canonical little-endian; uses bases [0, count); result -> d_result (XYZZ)
   void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, cudaStream_t st);
+  // stage timing (bench.py's roofline leg): when `profile` is set, run() brackets its stages with
+  // CUDA events on the launching stream; stage_ms() reads them after the stream has drained.
+  // stages: 0 digits+scan+scatter, 1 accumulate, 2 bucket reduce, 3 window combine
+  bool profile = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  void stage_ms(float out[4]);
+  ~BaseTable();
   size_t device_bytes() const;
 };
 

@@ -88,6 +88,51 @@ int api_msm_oneshot(const uint8_t* bases, const uint8_t* inf_flags, const uint8_
   ZK_API_END
 }
 
+// sum of k points given in the uncompressed wire format (the shards' partial sums), one thread
+template <class T>
+__global__ void k_sum_raw(const uint8_t* __restrict__ raw, uint32_t k, XYZZ<typename T::F>* __restrict__ out, int* err) {
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ<typename T::F> acc = XYZZ<typename T::F>::inf();
+  for (uint32_t i = 0; i < k; i++) {
+    Affine<typename T::F> p;
+    if (T::parse(raw + (size_t)i * T::RAW, p)) { if (err) atomicExch(err, 1); continue; }
+    acc.madd(p);
+  }
+  store_vec(out, acc);
+}
+
+template <class T>
+int api_sum_dev(const void* d_points, size_t k, void* d_out, void* stream) {
+  ZK_API_BEGIN
+  ZK_REQUIRE(d_points && d_out && k > 0 && k <= 4096, ZK_EARG, "sum_dev: bad arguments");
+  cudaStream_t st = stream ? (cudaStream_t)stream : default_stream();
+  static thread_local DevBuf<XYZZ<typename T::F>> scratch;
+  scratch.ensure(1);
+  k_sum_raw<T><<<1, 32, 0, st>>>((const uint8_t*)d_points, (uint32_t)k, scratch.p, nullptr);
+  finalize_points<T>(scratch.p, 1, (uint8_t*)d_out, st);
+  ZK_API_END
+}
+
+template <class T>
+int api_sum(const uint8_t* points, size_t k, uint8_t* out) {
+  ZK_API_BEGIN
+  ZK_REQUIRE(points && out && k > 0 && k <= 4096, ZK_EARG, "sum: bad arguments");
+  cudaStream_t st = default_stream();
+  DevBuf<uint8_t> d_in(k * T::RAW), d_out(T::RAW + T::COMP);
+  DevBuf<XYZZ<typename T::F>> d_acc(1);
+  DevBuf<int> d_err(1);
+  ZK_CUDA(cudaMemcpyAsync(d_in.p, points, k * T::RAW, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+  k_sum_raw<T><<<1, 32, 0, st>>>(d_in.p, (uint32_t)k, d_acc.p, d_err.p);
+  finalize_points<T>(d_acc.p, 1, d_out.p, st);
+  int err = 0;
+  ZK_CUDA(cudaMemcpyAsync(out, d_out.p, T::RAW + T::COMP, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(err == 0, ZK_EPOINT, "sum: point not canonical or not on the curve");
+  ZK_API_END
+}
+
 // out[i] = scalars[i] * generator, uncompressed
 template <class T>
 __global__ void __launch_bounds__(128)

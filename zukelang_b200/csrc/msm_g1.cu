@@ -31,4 +31,8 @@ int zk_g1_table_msm_dev(uint64_t handle, const void* d_scalars, size_t n, void* 
 int zk_g1_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out) {
   return zk::api_fixed_base_mul<G1Traits>(scalars, n, out);
 }
+int zk_g1_sum(const uint8_t* points, size_t k, uint8_t* out) { return zk::api_sum<G1Traits>(points, k, out); }
+int zk_g1_sum_dev(const void* d_points, size_t k, void* d_out, void* stream) {
+  return zk::api_sum_dev<G1Traits>(d_points, k, d_out, stream);
+}
 }

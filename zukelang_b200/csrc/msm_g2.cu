@@ -24,4 +24,8 @@ int zk_g2_table_msm_dev(uint64_t handle, const void* d_scalars, size_t n, void* 
 int zk_g2_fixed_base_mul(const uint8_t* scalars, size_t n, uint8_t* out) {
   return zk::api_fixed_base_mul<G2Traits>(scalars, n, out);
 }
+int zk_g2_sum(const uint8_t* points, size_t k, uint8_t* out) { return zk::api_sum<G2Traits>(points, k, out); }
+int zk_g2_sum_dev(const void* d_points, size_t k, void* d_out, void* stream) {
+  return zk::api_sum_dev<G2Traits>(d_points, k, d_out, stream);
+}
 }

@@ -118,6 +118,10 @@ template <class T>
 void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, cudaStream_t st) {
   ZK_REQUIRE(count > 0 && count <= n, ZK_EARG, "scalar count exceeds the base table");
   const uint32_t nb = cfg.nbuckets();
+  if (profile && !ev[0])
+    for (auto& e : ev) ZK_CUDA(cudaEventCreate(&e));
+  auto mark = [&](int i) { if (profile) ZK_CUDA(cudaEventRecord(ev[i], st)); };
+  mark(0);
   ZK_CUDA(cudaMemsetAsync(counts.p, 0, nb * sizeof(uint32_t), st));
   k_digits<false><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, counts.p, nullptr);
   uint32_t ntiles = cdiv(nb, SCAN_TILE);
@@ -125,13 +129,31 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   k_scan_spine<<<1, 1024, 0, st>>>(tile_sums.p, ntiles);
   k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p, offsets.p, cursor.p);
   k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, cursor.p, entries.p);
+  mark(1);
   uint32_t nthreads = nb * cfg.S;
   k_accumulate<F><<<cdiv(nthreads, 128), 128, 0, st>>>(pts.p, entries.p, offsets.p, parts.p, nb, cfg.S);
+  mark(2);
   uint32_t cpw = cfg.B / cfg.L;
   k_reduce_chunks<F><<<cdiv((size_t)cpw * cfg.nwb, 128), 128, 0, st>>>(parts.p, cfg, chunk_out.p);
   k_reduce_tree<F><<<cfg.nwb, 128, 128 * sizeof(XYZZ<F>), st>>>(chunk_out.p, cpw, window_sums.p);
+  mark(3);
   k_horner<F><<<1, 32, 0, st>>>(window_sums.p, cfg, d_result);
+  mark(4);
   ZK_CUDA(cudaGetLastError());
+}
+
+template <class T>
+void BaseTable<T>::stage_ms(float out[4]) {
+  for (int i = 0; i < 4; i++) {
+    out[i] = 0.f;
+    if (ev[0]) ZK_CUDA(cudaEventElapsedTime(&out[i], ev[i], ev[i + 1]));
+  }
+}
+
+template <class T>
+BaseTable<T>::~BaseTable() {
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
 }
 
 template <class T>
