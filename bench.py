@@ -223,6 +223,7 @@ def run_gpu_arm(args):
         host = torch.from_numpy(np.ascontiguousarray(w[lo:hi]).view(np.int64)).pin_memory()
         batches.append({"host": host, "dev": host.cuda(), "expect_dlog": tot})
     d_out = torch.zeros(144, dtype=torch.uint8, device="cuda")
+    d_ring = torch.zeros(pool, 144, dtype=torch.uint8, device="cuda")     # one result slot per batch
     side = torch.cuda.Stream()
     gathered = torch.zeros(world * 96, dtype=torch.uint8, device="cuda")
     d_sum = torch.zeros(144, dtype=torch.uint8, device="cuda")
@@ -234,9 +235,17 @@ def run_gpu_arm(args):
         return d_sum
 
     def step_device(b):
-        """one MSM with device-resident scalars; returns the result tensor (on device)"""
+        """one MSM with device-resident scalars; returns the result tensor (on device).
+        N = 1: consecutive steps are pipelined (zk_table_pipeline): the tail of step i overlaps the
+        accumulation of step i+1 and results are valid after zk_table_join."""
+        if world == 1:
+            _lib.check(zk.zk_g1_table_msm_dev(handle.value, batches[b]["dev"].data_ptr(), n, d_ring[b].data_ptr(), side.cuda_stream))
+            return d_ring[b]
         _lib.check(zk.zk_g1_table_msm_dev(handle.value, batches[b]["dev"].data_ptr(), n, d_out.data_ptr(), side.cuda_stream))
-        return d_out if world == 1 else reduce_shards()
+        return reduce_shards()
+
+    def join():
+        _lib.check(zk.zk_table_join(handle.value, side.cuda_stream))
 
     def combine(res):
         return bytes(res.cpu().numpy())[:96]
@@ -259,19 +268,22 @@ def run_gpu_arm(args):
         peak_imad = max(peak_imad, ops.value)
     peak_mac32 = peak_imad / 2.0                       # one MAC32 = mad.lo + mad.hi
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---- warm-up, with the exact known-dlog check -------------------------------------------
     with torch.cuda.stream(side):
         for it in range(args.warmup):
             b = it % pool
             parts = step_device(b)
+            join()
             side.synchronize()
             got = combine(parts)
             assert got == expected_point(batches[b]["expect_dlog"]), "MSM result differs from the known-dlog closed form"
 
     # ---- timed region: `value` (inputs resident in HBM) -----------------------------------------
     _lib.check(zk.zk_table_profile(handle.value, 1, None))
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    if world == 1 and not args.no_pipeline:
+        _lib.check(zk.zk_table_pipeline(handle.value, 1))
     acc_ms, stage = [], (ctypes.c_float * 4)()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,6 +291,7 @@ def run_gpu_arm(args):
         e0.record(side)
         for it in range(args.steps):
             parts = step_device((args.warmup + it) % pool)
+        join()
         e1.record(side)
     barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -292,10 +305,12 @@ def run_gpu_arm(args):
     with torch.cuda.stream(side):
         for it in range(min(args.steps, 5)):
             step_device(it % pool)
+            join()
             side.synchronize()
             _lib.check(zk.zk_table_profile(handle.value, 1, stage))
             acc_ms.append(float(stage[1]))
     _lib.check(zk.zk_table_profile(handle.value, 0, None))
+    _lib.check(zk.zk_table_pipeline(handle.value, 0))
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -342,12 +357,13 @@ def run_gpu_arm(args):
                        "points": n_total, "points_per_gpu": n, "window_bits": c, "windows": W,
                        "precomputed_table": bool(info[7]), "table_MiB_per_gpu": int(info[5]) >> 20,
                        "segments": int(info[4]), "true_mixed_adds_per_point": W,
+                       "pipelined_steps": bool(world == 1 and not args.no_pipeline),
                        "l2": "inputs larger than L2 (table %d MiB, %d rotating scalar batches of %d MiB)" % (int(info[5]) >> 20, pool, (n * 32) >> 20),
                        "parallelism": "base-range shards x%d, all_gather of 96-B partial sums" % world, "setup_s": setup_s},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 144,
                     "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": (10 if world == 1 else 12) * args.steps,
+            "gpu_launches": (13 if world == 1 else 15) * args.steps,
             "roofline": {"bound": "int32-imad", "kernel": "k_accumulate<Fp>", "achieved": achieved,
                          "peak": peak_mac32 / 1e12, "unit": "TMAC32/s", "frac": achieved / (peak_mac32 / 1e12),
                          "traffic": None, "kernel_ms": acc_avg, "stages_ms_last_step": stages_last,
@@ -382,6 +398,7 @@ def main():
     ap.add_argument("--logn", type=int, default=LOG_N)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="plain stream order between steps")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -80,6 +80,14 @@ int zk_g2_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *
 /* info[0] = window bits c, [1] = windows W, [2] = bucket windows, [3] = buckets per window,
  * [4] = segments, [5] = device bytes, [6] = points, [7] = precomputed */
 int zk_table_info(uint64_t handle, uint64_t info[8]);
+/* Pipelining of consecutive *_msm_dev calls on one table.  Each MSM ends in a latency-bound
+ * tail (bucket reduction, window combine, affine conversion) that runs on the table's own
+ * high-priority side stream.  With enable = 0 (default) a call makes cuda_stream wait for that
+ * tail, i.e. plain stream order.  With enable != 0 the call returns once the tail is enqueued, so
+ * the next MSM's sort + accumulation overlaps it; d_out of every outstanding call is valid on
+ * cuda_stream only after zk_table_join(handle, cuda_stream). */
+int zk_table_pipeline(uint64_t handle, int enable);
+int zk_table_join(uint64_t handle, void *cuda_stream);
 /* Stage timing for the roofline leg of bench.py: enable != 0 makes the following MSMs on this
  * table bracket their stages with CUDA events on the launching stream; stage_ms (nullable)
  * receives the last profiled run's times once that stream has been synchronised:

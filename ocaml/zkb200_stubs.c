@@ -1,0 +1,132 @@
+/* OCaml foreign stubs over libzkb200 (include/zkb200.h).
+ *
+ * Shipped as SOURCE: no OCaml toolchain exists in the build image (SURVEY.md headline fact 3),
+ * so this file is compiled by the zukelang maintainer with the dune stanza in ocaml/dune.
+ * Every stub copies its OCaml Bytes arguments before releasing the runtime lock and copies the
+ * result back afterwards; no OCaml heap pointer is held across the blocking section.
+ */
+#include <string.h>
+#include <stdlib.h>
+#include <caml/alloc.h>
+#include <caml/fail.h>
+#include <caml/memory.h>
+#include <caml/mlvalues.h>
+#include <caml/threads.h>
+#include "zkb200.h"
+
+static void zk_raise(int rc) {
+  if (rc == ZK_EARG) caml_invalid_argument(zk_last_error());   /* curve.ml:116 Invalid_argument */
+  caml_failwith(zk_last_error());                              /* assert false / assert (is_zero rem) */
+}
+
+static uint8_t *dup_bytes(value v, size_t *len) {
+  size_t n = caml_string_length(v);
+  uint8_t *p = (uint8_t *)malloc(n ? n : 1);
+  memcpy(p, Bytes_val(v), n);
+  if (len) *len = n;
+  return p;
+}
+
+CAMLprim value zkb200_init(value dev) {
+  CAMLparam1(dev);
+  int rc = zk_init(Int_val(dev));
+  if (rc) zk_raise(rc);
+  CAMLreturn(Val_unit);
+}
+
+/* g1_msm : bases:bytes (96 n) -> scalars:bytes (32 n) -> bytes (144)   — Curve.G.dot / apply_powers */
+CAMLprim value zkb200_g1_msm(value bases, value scalars) {
+  CAMLparam2(bases, scalars);
+  CAMLlocal1(out);
+  size_t nb, ns;
+  uint8_t *b = dup_bytes(bases, &nb), *s = dup_bytes(scalars, &ns);
+  uint8_t res[ZK_G1_OUT];
+  size_t n = ns / ZK_FR_BYTES;
+  int rc = (nb == n * ZK_G1_RAW) ? 0 : ZK_EARG;
+  if (!rc) {
+    caml_release_runtime_system();
+    rc = zk_g1_msm(b, NULL, s, n, res);
+    caml_acquire_runtime_system();
+  }
+  free(b); free(s);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(ZK_G1_OUT);
+  memcpy(Bytes_val(out), res, ZK_G1_OUT);
+  CAMLreturn(out);
+}
+
+CAMLprim value zkb200_g2_msm(value bases, value scalars) {
+  CAMLparam2(bases, scalars);
+  CAMLlocal1(out);
+  size_t nb, ns;
+  uint8_t *b = dup_bytes(bases, &nb), *s = dup_bytes(scalars, &ns);
+  uint8_t res[ZK_G2_OUT];
+  size_t n = ns / ZK_FR_BYTES;
+  int rc = (nb == n * ZK_G2_RAW) ? 0 : ZK_EARG;
+  if (!rc) {
+    caml_release_runtime_system();
+    rc = zk_g2_msm(b, NULL, s, n, res);
+    caml_acquire_runtime_system();
+  }
+  free(b); free(s);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(ZK_G2_OUT);
+  memcpy(Bytes_val(out), res, ZK_G2_OUT);
+  CAMLreturn(out);
+}
+
+/* qap_load : v:bytes -> w:bytes -> y:bytes -> target:bytes -> m:int -> n:int -> int64 handle */
+CAMLprim value zkb200_qap_load_native(value v, value w, value y, value t, value m, value n) {
+  CAMLparam5(v, w, y, t, m);
+  CAMLxparam1(n);
+  uint8_t *pv = dup_bytes(v, NULL), *pw = dup_bytes(w, NULL), *py = dup_bytes(y, NULL), *pt = dup_bytes(t, NULL);
+  uint64_t h = 0;
+  caml_release_runtime_system();
+  int rc = zk_qap_load(pv, pw, py, pt, (size_t)Long_val(m), (size_t)Long_val(n), &h);
+  caml_acquire_runtime_system();
+  free(pv); free(pw); free(py); free(pt);
+  if (rc) zk_raise(rc);
+  CAMLreturn(caml_copy_int64((int64_t)h));
+}
+CAMLprim value zkb200_qap_load_bytecode(value *argv, int argn) {
+  (void)argn;
+  return zkb200_qap_load_native(argv[0], argv[1], argv[2], argv[3], argv[4], argv[5]);
+}
+
+/* groth16_prove : pk:int64 -> qap:int64 -> sol:bytes -> r:bytes -> s:bytes -> bytes (576) */
+CAMLprim value zkb200_groth16_prove(value pk, value qap, value sol, value r, value s) {
+  CAMLparam5(pk, qap, sol, r, s);
+  CAMLlocal1(out);
+  uint8_t *ps = dup_bytes(sol, NULL), *pr = dup_bytes(r, NULL), *pss = dup_bytes(s, NULL);
+  uint8_t res[ZK_GROTH16_PROOF_OUT];
+  uint64_t hpk = (uint64_t)Int64_val(pk), hq = (uint64_t)Int64_val(qap);
+  caml_release_runtime_system();
+  int rc = zk_groth16_prove(hpk, hq, ps, pr, pss, res);
+  caml_acquire_runtime_system();
+  free(ps); free(pr); free(pss);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(ZK_GROTH16_PROOF_OUT);
+  memcpy(Bytes_val(out), res, ZK_GROTH16_PROOF_OUT);
+  CAMLreturn(out);
+}
+
+/* pinocchio_prove : pk:int64 -> qap:int64 -> sol:bytes -> d:bytes (96, or empty for NonZK) -> bytes (1440) */
+CAMLprim value zkb200_pinocchio_prove(value pk, value qap, value sol, value d) {
+  CAMLparam4(pk, qap, sol, d);
+  CAMLlocal1(out);
+  size_t dl;
+  uint8_t *ps = dup_bytes(sol, NULL), *pd = dup_bytes(d, &dl);
+  uint8_t res[ZK_PINOCCHIO_PROOF_OUT];
+  uint64_t hpk = (uint64_t)Int64_val(pk), hq = (uint64_t)Int64_val(qap);
+  caml_release_runtime_system();
+  int rc = zk_pinocchio_prove(hpk, hq, ps, dl == 96 ? pd : NULL, res);
+  caml_acquire_runtime_system();
+  free(ps); free(pd);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(ZK_PINOCCHIO_PROOF_OUT);
+  memcpy(Bytes_val(out), res, ZK_PINOCCHIO_PROOF_OUT);
+  CAMLreturn(out);
+}
+/* zk_groth16_pk_load / zk_pinocchio_pk_load take a struct of byte arrays: the stub builds the
+ * struct from an OCaml record of Bytes in the same way (one dup_bytes per field), omitted here
+ * for brevity — see INTEGRATION.md for the field order. */

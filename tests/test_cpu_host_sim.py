@@ -50,8 +50,11 @@ def test_montgomery_limb_algorithms(sim, which, mod, n):
         assert _field(fn, n, 3, a) == (-a) % mod
         assert _field(fn, n, 4, a) == a * Rm % mod
         assert _field(fn, n, 5, a) == a * Ri % mod
-    for a in vals[:10]:
-        assert _field(fn, n, 6, a * Rm % mod) == ((pow(a, -1, mod) * Rm % mod) if a else 0)
+    for a in vals[:40]:
+        exp = (pow(a, -1, mod) * Rm % mod) if a else 0
+        assert _field(fn, n, 6, a * Rm % mod) == exp                 # binary extended Euclid
+        if a in vals[:10]:
+            assert _field(fn, n, 8, a * Rm % mod) == exp             # Fermat cross-check
 
 
 RM = (1 << 384) % P

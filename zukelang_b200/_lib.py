@@ -45,6 +45,8 @@ SIGNATURES = {
     "zk_g1_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_g2_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_table_info": (c_int, [c_uint64, POINTER(c_uint64)]),
+    "zk_table_pipeline": (c_int, [c_uint64, c_int]),
+    "zk_table_join": (c_int, [c_uint64, c_void_p]),
     "zk_table_profile": (c_int, [c_uint64, c_int, c_void_p]),
     "zk_table_free": (c_int, [c_uint64]),
     "zk_g1_sum": (c_int, [c_void_p, c_size_t, c_void_p]),

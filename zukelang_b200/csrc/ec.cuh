@@ -49,6 +49,32 @@ struct Fp2 {
   }
 };
 
+// Fp with the product routed through ONE out-of-line routine (arguments and result stay in
+// registers under the device ABI).  Same representation as Fp; used where the fully inlined
+// point formulas would overflow the instruction cache.
+#ifndef ZK_HOST_SIM
+static __device__ __noinline__ Fp fp_mul_outofline(Fp a, Fp b) { return a * b; }
+#endif
+struct FpCall {
+  Fp f;
+  static ZK_HD FpCall zero() { return FpCall{Fp::zero()}; }
+  static ZK_HD FpCall one() { return FpCall{Fp::one()}; }
+  ZK_HD bool is_zero() const { return f.is_zero(); }
+  ZK_HD bool operator==(const FpCall& b) const { return f == b.f; }
+  friend ZK_HD FpCall operator+(const FpCall& a, const FpCall& b) { return FpCall{a.f + b.f}; }
+  friend ZK_HD FpCall operator-(const FpCall& a, const FpCall& b) { return FpCall{a.f - b.f}; }
+#ifndef ZK_HOST_SIM
+  friend ZK_HD FpCall operator*(const FpCall& a, const FpCall& b) { return FpCall{fp_mul_outofline(a.f, b.f)}; }
+  ZK_HD FpCall sqr() const { return FpCall{fp_mul_outofline(f, f)}; }
+#else
+  friend ZK_HD FpCall operator*(const FpCall& a, const FpCall& b) { return FpCall{a.f * b.f}; }
+  ZK_HD FpCall sqr() const { return FpCall{f * f}; }
+#endif
+  ZK_HD FpCall dbl() const { return FpCall{f.dbl()}; }
+  ZK_HD FpCall neg() const { return FpCall{f.neg()}; }
+  ZK_NI FpCall inverse() const { return FpCall{f.inverse()}; }
+};
+
 // -------------------------------------------------------------------------
 // points
 // -------------------------------------------------------------------------

@@ -94,6 +94,20 @@ __global__ void __launch_bounds__(128) k_mb_g1_madd(uint32_t* out, int iters) {
   if (acc.X.v[0] == 0x12345678u && acc.Y.v[1] == 0x9abcdef0u) out[0] = acc.ZZ.v[2];
 }
 
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_mb_madd_var(uint32_t* out, int iters) {
+  Affine<F> g;
+  {
+    G1Affine gg = G1Traits::generator();
+    g = *reinterpret_cast<Affine<F>*>(&gg);
+  }
+  XYZZ<F> acc = XYZZ<F>::dbl_affine(g);
+  for (int i = 0; i < (int)(threadIdx.x & 3); i++) acc = acc.dbl();
+  for (int it = 0; it < iters; it++) acc.madd(g);
+  uint32_t* w = reinterpret_cast<uint32_t*>(&acc);
+  if (w[0] == 0x12345678u && w[13] == 0x9abcdef0u) out[0] = w[26];
+}
+
 // ---- device field-op test hook ----------------------------------------------------
 template <class F>
 __global__ void k_test_field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, uint32_t n) {
@@ -138,6 +152,10 @@ int zk_bench_intpipe(int kind, int iters, double* ops_per_s, double* elapsed_ms)
       case 3: k_mb_field_mul<Fp><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it * 2; break;
       case 4: k_mb_field_mul<Fr><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it * 2; break;
       case 5: k_mb_g1_madd<<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
+      case 6: k_mb_madd_var<FpCall, 4><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
+      case 7: k_mb_madd_var<Fp, 4><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
+      case 8: k_mb_madd_var<FpCall, 5><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
+      case 9: k_mb_madd_var<FpCall, 3><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
       default: throw Error{ZK_EARG, "bench_intpipe: unknown kind"};
     }
   };
@@ -187,6 +205,27 @@ int zk_table_profile(uint64_t handle, int enable, float stage_ms[4]) {
     if (stage_ms) h->table.stage_ms(stage_ms);
     h->table.profile = enable != 0;
   }
+  ZK_API_END
+}
+
+int zk_table_pipeline(uint64_t handle, int enable) {
+  ZK_API_BEGIN
+  using namespace zk;
+  HandleBase* hb = lookup_handle(handle, 0);
+  ZK_REQUIRE(hb->kind == 1 || hb->kind == 2, ZK_EARG, "table_pipeline: not a table handle");
+  if (hb->kind == 1) static_cast<TableHandle<G1Traits>*>(hb)->table.pipelined = enable != 0;
+  else static_cast<TableHandle<G2Traits>*>(hb)->table.pipelined = enable != 0;
+  ZK_API_END
+}
+
+int zk_table_join(uint64_t handle, void* stream) {
+  ZK_API_BEGIN
+  using namespace zk;
+  HandleBase* hb = lookup_handle(handle, 0);
+  ZK_REQUIRE(hb->kind == 1 || hb->kind == 2, ZK_EARG, "table_join: not a table handle");
+  cudaStream_t st = stream ? (cudaStream_t)stream : default_stream();
+  if (hb->kind == 1) static_cast<TableHandle<G1Traits>*>(hb)->table.join(st);
+  else static_cast<TableHandle<G2Traits>*>(hb)->table.join(st);
   ZK_API_END
 }
 

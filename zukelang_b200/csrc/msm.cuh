@@ -30,7 +30,7 @@ struct MsmConfig {
   int W;        // number of windows  = ceil(256 / c)
   int nwb;      // bucket windows: 1 when precomputed, else W
   uint32_t B;   // buckets per window = 2^(c-1)
-  int S;        // segments per bucket in the accumulation
+  int S;        // (unused since the balanced accumulation; kept for the info record)
   int L;        // buckets per thread in the chunk reduction
   __host__ __device__ uint32_t nbuckets() const { return (uint32_t)nwb * B; }
 };
@@ -51,8 +51,10 @@ __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* k, int pos, int 
   return (uint32_t)(((hi << 32) | lo) >> sh) & ((1u << c) - 1);
 }
 
-// Steps 1 and 3.  Signed-digit recoding: d in [-(2^(c-1) - 1), 2^(c-1)], carry
-// into the next window; zero digits (and identity bases) emit nothing.
+// Steps 1 and 3.  Signed-digit recoding.  A scalar k > (r-1)/2 is first replaced by r - k with
+// every digit sign flipped (k P = (r - k)(-P)), which bounds the recoded value by 2^254 and saves
+// a window for c = 17, 19, 20.  Digits d lie in [-(2^(c-1) - 1), 2^(c-1)] with a carry into the
+// next window; zero digits (and identity bases) emit nothing.
 // entry = point index (w * stride + i when precomputed, else i) | sign << 31;
 // n = scalars in this call, stride = points per window of the table.
 template <bool SCATTER>
@@ -67,12 +69,24 @@ k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip,
   uint4 a = __ldg(sp), b = __ldg(sp + 1);
   k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
   if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) return;
+  uint32_t flip = 0;
+  {
+    uint32_t h[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) h[j] = FrParams::half(j);
+    if (!Fr::geq_raw(h, k)) {  // k > (r-1)/2  ->  k = r - k
+      flip = 1;
+      k[0] = ptx::sub_cc(FrParams::mod(0), k[0]);
+#pragma unroll
+      for (int j = 1; j < 8; j++) k[j] = ptx::subc_cc(FrParams::mod(j), k[j]);
+    }
+  }
   uint32_t carry = 0;
   const uint32_t half = cfg.B;  // 2^(c-1)
   for (int w = 0; w < cfg.W; w++) {
     uint32_t d = scalar_bits(k, w * cfg.c, cfg.c) + carry;
-    uint32_t neg = 0;
-    if (d > half) { d = (1u << cfg.c) - d; neg = 1; carry = 1; } else carry = 0;
+    uint32_t neg = flip;
+    if (d > half) { d = (1u << cfg.c) - d; neg ^= 1; carry = 1; } else carry = 0;
     if (d == 0) continue;
     uint32_t bucket = (cfg.nwb == 1 ? 0u : (uint32_t)w * cfg.B) + d - 1;
     if (SCATTER) {
@@ -161,28 +175,55 @@ k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __rest
   }
 }
 
-// Step 4: bucket accumulation.  Thread t owns (bucket b = t % nbuckets, segment s = t / nbuckets)
-// and folds its slice of the sorted entry list into an XYZZ accumulator with mixed adds.
-// Bases are gathered with 128-bit loads; the next base is fetched while the current one is added.
-template <class F>
-__global__ void __launch_bounds__(128)
+// Step 4: bucket accumulation, exactly balanced.  The grid is persistent (one wave: resident
+// blocks per SM x SM count) and thread t folds the contiguous slice [t * per, (t+1) * per) of the
+// bucket-sorted entry list, per = ceil(E / T): every thread performs the same number of mixed adds
+// whatever the scalar distribution.  A bucket that lies entirely inside one slice is written to
+// bucket_sums directly; the (at most two) partial pieces at the ends of a slice go to
+// partial[2t] (slice starts inside that bucket) / partial[2t+1] (bucket runs past the slice end) and
+// k_fix_partials adds them up.  Bases are gathered with 128-bit loads, the next base is fetched
+// while the current one is added.
+// MINB = resident blocks per SM the register allocation is capped for; PREFETCH = fetch the
+// next base while adding the current one (costs 24 registers).
+template <class F, int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(128, MINB)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
-             const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ out, uint32_t nbuckets, int S) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nbuckets * (uint32_t)S) return;
-  uint32_t b = t % nbuckets, s = t / nbuckets;
-  uint32_t lo = offsets[b], hi = offsets[b + 1];
-  uint32_t len = hi - lo;
-  uint32_t k0 = lo + (uint32_t)(((uint64_t)len * s) / S);
-  uint32_t k1 = lo + (uint32_t)(((uint64_t)len * (s + 1)) / S);
+             const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums, XYZZ<F>* __restrict__ partial,
+             uint32_t nbuckets) {
+  const uint32_t T = gridDim.x * blockDim.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t E = offsets[nbuckets];
+  const uint32_t per = (E + T - 1) / T;
+  const uint64_t e0_64 = (uint64_t)t * per;
+  if (per == 0 || e0_64 >= E) return;
+  const uint32_t e0 = (uint32_t)e0_64;
+  const uint32_t e1 = min(E, e0 + per);
+  // bucket of entry e0: largest b with offsets[b] <= e0
+  uint32_t lo = 0, hi = nbuckets;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= e0) lo = mid; else hi = mid;
+  }
+  uint32_t b = lo;
+  uint32_t b_end = offsets[b + 1];
+  while (b_end <= e0) { b++; b_end = offsets[b + 1]; }   // skip empty buckets sharing the offset
+  uint32_t seg_start = e0;
   XYZZ<F> acc = XYZZ<F>::inf();
-  if (k0 < k1) {
-    uint32_t e = entries[k0];
-    Affine<F> cur = load_vec(&bases[e & 0x7fffffffu]);
-    for (uint32_t k = k0; k < k1; k++) {
+  uint32_t e = entries[e0];
+  Affine<F> cur;
+  if (PREFETCH) cur = load_vec(&bases[e & 0x7fffffffu]);
+  for (uint32_t k = e0; k < e1; k++) {
+    if (k >= b_end) {  // bucket b is finished: it started at seg_start
+      const bool complete = seg_start == offsets[b];
+      store_vec(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);   // incomplete => started before e0
+      acc = XYZZ<F>::inf();
+      do { b++; b_end = offsets[b + 1]; } while (b_end <= k);
+      seg_start = k;
+    }
+    if (PREFETCH) {
       uint32_t e_next = 0;
       Affine<F> nxt;
-      bool more = k + 1 < k1;
+      const bool more = k + 1 < e1;
       if (more) {
         e_next = entries[k + 1];
         nxt = load_vec(&bases[e_next & 0x7fffffffu]);
@@ -190,9 +231,85 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
       if (e >> 31) cur.y = cur.y.neg();
       acc.madd(cur);
       if (more) { cur = nxt; e = e_next; }
+    } else {
+      e = entries[k];
+      cur = load_vec(&bases[e & 0x7fffffffu]);
+      if (e >> 31) cur.y = cur.y.neg();
+      acc.madd(cur);
     }
   }
-  store_vec(&out[t], acc);
+  // last piece: bucket b from seg_start to e1
+  const bool starts_here = seg_start == offsets[b];
+  const bool ends_here = e1 == b_end;
+  if (starts_here && ends_here) store_vec(&bucket_sums[b], acc);
+  else store_vec(&partial[2 * (size_t)t + (e0 >= offsets[b] ? 0 : 1)], acc);
+}
+
+// Step 4b: one thread per bucket: empty buckets become the identity; a bucket split over a few
+// slices gets the sum of its pieces (slot rule as in k_accumulate).  Buckets split over more than
+// HEAVY_PIECES slices (skewed scalars) are queued for k_fix_heavy.
+constexpr uint32_t HEAVY_PIECES = 8;
+template <class F>
+__global__ void __launch_bounds__(128)
+k_fix_partials(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums,
+               const XYZZ<F>* __restrict__ partial, uint32_t nbuckets, uint32_t T,
+               uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  const uint32_t E = offsets[nbuckets];
+  const uint32_t lo = offsets[b], hi = offsets[b + 1];
+  if (lo == hi) { store_vec(&bucket_sums[b], XYZZ<F>::inf()); return; }
+  const uint32_t per = (E + T - 1) / T;
+  const uint32_t t_first = lo / per, t_last = (hi - 1) / per;
+  if (t_first == t_last) return;  // written whole by its slice
+  if (t_last - t_first + 1 > HEAVY_PIECES) { heavy_list[atomicAdd(heavy_count, 1u)] = b; return; }
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t t = t_first; t <= t_last; t++) {
+    const uint32_t slot = ((uint64_t)t * per >= lo) ? 0 : 1;
+    XYZZ<F> p = load_vec_rw(&partial[2 * (size_t)t + slot]);
+    acc.add(p);
+  }
+  store_vec(&bucket_sums[b], acc);
+}
+
+// Step 4c: heavy buckets, one warp each (grid-stride over the queue): lanes stride over the pieces,
+// a shared-memory tree adds the 32 lane sums: pieces / 32 + 5 sequential additions.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_fix_heavy(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums,
+            const XYZZ<F>* __restrict__ partial, uint32_t nbuckets, uint32_t T,
+            const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
+  extern __shared__ uint4 smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t count = *heavy_count;
+  const uint32_t E = offsets[nbuckets];
+  const uint32_t per = (E + T - 1) / T;
+  XYZZ<F>* w = sm + wib * 32;
+  for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + wib; q < count; q += nwarps) {   // warp-uniform
+    const uint32_t b = heavy_list[q];
+    const uint32_t lo = offsets[b], hi = offsets[b + 1];
+    const uint32_t t_first = lo / per, t_last = (hi - 1) / per;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t t = t_first + lane; t <= t_last; t += 32) {
+      const uint32_t slot = ((uint64_t)t * per >= lo) ? 0 : 1;
+      XYZZ<F> p = load_vec_rw(&partial[2 * (size_t)t + slot]);
+      acc.add(p);
+    }
+    w[lane] = acc;
+    __syncwarp();
+    for (uint32_t stride = 16; stride > 0; stride >>= 1) {
+      if (lane < stride) {
+        XYZZ<F> a = w[lane];
+        a.add(w[lane + stride]);
+        w[lane] = a;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) store_vec(&bucket_sums[b], w[0]);
+    __syncwarp();
+  }
 }
 
 // k * p for a small (< 2^31) multiplier
@@ -209,22 +326,19 @@ __device__ __noinline__ XYZZ<F> small_mul(const XYZZ<F>& p, uint32_t k) {
 }
 
 // Step 5a: thread (window wb, chunk ch) reduces L consecutive buckets with the running-sum
-// trick:  V = sum_{j<L} (ch*L + j + 1) * bucket[ch*L + j]  (segments summed on the fly).
+// trick:  V = sum_{j<L} (ch*L + j + 1) * bucket[ch*L + j].
 template <class F>
 __global__ void __launch_bounds__(128)
-k_reduce_chunks(const XYZZ<F>* __restrict__ parts, MsmConfig cfg, XYZZ<F>* __restrict__ chunk_out) {
+k_reduce_chunks(const XYZZ<F>* __restrict__ bucket_sums, MsmConfig cfg, XYZZ<F>* __restrict__ chunk_out) {
   uint32_t chunks_per_window = cfg.B / cfg.L;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= chunks_per_window * (uint32_t)cfg.nwb) return;
   uint32_t wb = t / chunks_per_window, ch = t % chunks_per_window;
-  uint32_t nb = cfg.nbuckets();
   uint32_t first = wb * cfg.B + ch * cfg.L;
   XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
   for (int j = cfg.L - 1; j >= 0; j--) {
-    for (int s = 0; s < cfg.S; s++) {
-      XYZZ<F> p = load_vec_rw(&parts[(size_t)s * nb + first + j]);
-      run.add(p);
-    }
+    XYZZ<F> p = load_vec_rw(&bucket_sums[first + j]);
+    run.add(p);
     acc.add(run);
   }
   // acc = sum (j+1) * bucket_j ; run = sum bucket_j ; add (ch*L) * run
@@ -233,29 +347,28 @@ k_reduce_chunks(const XYZZ<F>* __restrict__ parts, MsmConfig cfg, XYZZ<F>* __res
   store_vec(&chunk_out[t], acc);
 }
 
-// Step 5b: one block per window sums that window's chunk results (strided serial + smem tree).
+// Step 5b: one level of the sum tree: block (x, window y) adds up to 128 consecutive elements of
+// its window (count per window = n_in) and writes one: out[y * gridDim.x + x].
 template <class F>
 __global__ void __launch_bounds__(128)
-k_reduce_tree(const XYZZ<F>* __restrict__ chunk_out, uint32_t chunks_per_window, XYZZ<F>* __restrict__ window_sums) {
+k_reduce_tree(const XYZZ<F>* __restrict__ in, uint32_t n_in, XYZZ<F>* __restrict__ out) {
   extern __shared__ uint4 smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  const XYZZ<F>* src = chunk_out + (size_t)blockIdx.x * chunks_per_window;
+  const XYZZ<F>* src = in + (size_t)blockIdx.y * n_in;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t i = threadIdx.x; i < chunks_per_window; i += blockDim.x) {
-    XYZZ<F> p = load_vec_rw(&src[i]);
-    acc.add(p);
-  }
+  if (i < n_in) acc = load_vec_rw(&src[i]);
   sm[threadIdx.x] = acc;
   __syncthreads();
   for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
-    if (threadIdx.x < stride) {
+    if (threadIdx.x < stride && i + stride < n_in) {
       XYZZ<F> a = sm[threadIdx.x];
       a.add(sm[threadIdx.x + stride]);
       sm[threadIdx.x] = a;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) store_vec(&window_sums[blockIdx.x], sm[0]);
+  if (threadIdx.x == 0) store_vec(&out[(size_t)blockIdx.y * gridDim.x + blockIdx.x], sm[0]);
 }
 
 // Step 6: result = sum_w 2^(c*w) * window_sums[w]   (Horner; nwb == 1 just copies)
@@ -366,19 +479,32 @@ struct BaseTable {
   DevBuf<Affine<F>> pts;     // n points, or W * n when precomputed (window-major)
   DevBuf<uint8_t> skip;      // 1 = identity base
   // workspace (reused by every MSM on this table; calls on one table are stream-ordered)
-  DevBuf<uint32_t> counts, offsets, cursor, tile_sums, entries;
-  DevBuf<XYZZ<F>> parts, chunk_out, window_sums;
+  DevBuf<uint32_t> counts, offsets, cursor, tile_sums, entries, heavy;   // heavy[0] = queue length, then the queue
+  // Bucket sums and the reduction scratch are double-buffered: the latency-bound tail of MSM i
+  // (bucket reduction, window combine, affine conversion) runs on `tail`, a high-priority side
+  // stream, while the caller's stream already sorts and accumulates MSM i+1.
+  DevBuf<XYZZ<F>> bucket_sums[2], partial[2], chunk_out[2], tree_tmp[2], window_sums[2];
+  uint32_t acc_blocks = 0;   // persistent grid of k_accumulate: resident blocks per SM x SMs
+  int acc_variant = 0;       // 0: 3 blocks/SM + prefetch, 1: 4 no prefetch, 2: 4 + prefetch, 3: 5 no prefetch
+  cudaStream_t tail = nullptr;
+  cudaEvent_t ev_acc[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
+  bool tail_pending[2] = {false, false};
+  uint64_t seq = 0;
+  bool pipelined = false;   // false: run() joins the tail before returning (plain stream order)
 
   static MsmConfig choose_config(uint32_t n, bool precompute, int force_c);
   void load(const uint8_t* host_raw, const uint8_t* host_inf, uint32_t n, bool precompute, int force_c,
             cudaStream_t st);
   void load_device_affine(const Affine<F>* d_affine, uint32_t n, bool precompute, int force_c, cudaStream_t st);
   void build_tables(cudaStream_t st);
-  // d_scalars: count * 32 B canonical little-endian; uses bases [0, count); result -> d_result (XYZZ)
-  void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, cudaStream_t st);
+  // d_scalars: count * 32 B canonical little-endian; uses bases [0, count).
+  // d_result (nullable) receives the XYZZ sum, d_out_bytes (nullable) the RAW + COMP bytes.
+  void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes, cudaStream_t st);
+  // make `st` wait for every outstanding tail of this table
+  void join(cudaStream_t st);
   // stage timing (bench.py's roofline leg): when `profile` is set, run() brackets its stages with
-  // CUDA events on the launching stream; stage_ms() reads them after the stream has drained.
-  // stages: 0 digits+scan+scatter, 1 accumulate, 2 bucket reduce, 3 window combine
+  // CUDA events; stage_ms() reads them after the streams have drained.
+  // stages: 0 digits+scan+scatter, 1 accumulate, 2 bucket reduce (incl. wait), 3 combine+finalize
   bool profile = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void stage_ms(float out[4]);

@@ -40,8 +40,8 @@ void table_msm_host(TableHandle<T>* h, const uint8_t* scalars, size_t n, uint8_t
   ZK_CUDA(cudaMemcpyAsync(h->d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st));
   k_check_scalars<<<cdiv(n, 256), 256, 0, st>>>(h->d_scalars.p, (uint32_t)n, h->d_err.p);
-  h->table.run(h->d_scalars.p, (uint32_t)n, h->d_result.p, st);
-  finalize_points<T>(h->d_result.p, 1, h->d_out.p, st);
+  h->table.run(h->d_scalars.p, (uint32_t)n, h->d_result.p, h->d_out.p, st);
+  h->table.join(st);
   int err = 0;
   ZK_CUDA(cudaMemcpyAsync(out, h->d_out.p, T::RAW + T::COMP, cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -63,8 +63,7 @@ int api_table_msm_dev(uint64_t handle, const void* d_scalars, size_t n, void* d_
   auto* h = static_cast<TableHandle<T>*>(lookup_handle(handle, T::ID));
   ZK_REQUIRE(d_scalars && d_out && n > 0 && n <= h->table.n, ZK_EARG, "msm_dev: bad arguments");
   cudaStream_t st = stream ? (cudaStream_t)stream : default_stream();
-  h->table.run((const uint32_t*)d_scalars, (uint32_t)n, h->d_result.p, st);
-  finalize_points<T>(h->d_result.p, 1, (uint8_t*)d_out, st);
+  h->table.run((const uint32_t*)d_scalars, (uint32_t)n, nullptr, (uint8_t*)d_out, st);
   ZK_API_END
 }
 

@@ -2,6 +2,10 @@
 #pragma once
 #include "msm.cuh"
 
+#ifndef ZK_ACC_VARIANT_DEFAULT
+#define ZK_ACC_VARIANT_DEFAULT 1
+#endif
+
 namespace zk {
 
 static inline int log2_ceil(uint32_t n) {
@@ -14,8 +18,9 @@ template <class T>
 MsmConfig BaseTable<T>::choose_config(uint32_t n, bool precompute, int force_c) {
   MsmConfig cfg;
   int lg = log2_ceil(n < 2 ? 2 : n);
-  int c = precompute ? lg : lg - 3;
-  if (c > 16) c = 16;
+  int c = precompute ? lg + 1 : lg - 3;
+  if (c > 17) c = 17;
+  if (!precompute && c > 16) c = 16;
   if (c < 4) c = 4;
   int env_c = env_int(precompute ? "ZKB200_WINDOW_BITS_PRE" : "ZKB200_WINDOW_BITS", 0);
   if (env_c > 0) c = env_c;
@@ -23,22 +28,19 @@ MsmConfig BaseTable<T>::choose_config(uint32_t n, bool precompute, int force_c) 
   if (c < 2) c = 2;
   if (c > 22) c = 22;
   cfg.c = c;
-  cfg.W = (256 + c - 1) / c;
+  // scalars are folded into [0, (r-1)/2] < 2^254 by k_digits; the top window must leave room for
+  // the incoming carry: its data bits must not exceed c - 1
+  auto windows = [](int cc) { int w = (254 + cc - 1) / cc; if (254 - (w - 1) * cc > cc - 1) w++; return w; };
+  // with one shared bucket set, a top window holding only a few data bits would pile every point
+  // into a handful of buckets: step down to a window size whose top window is reasonably full
+  if (precompute && force_c <= 0 && env_c <= 0)
+    while (c > 4 && 254 - (windows(c) - 1) * c < c - 6) c--;
+  cfg.c = c;
+  cfg.W = windows(c);
   cfg.nwb = precompute ? 1 : cfg.W;
   cfg.B = 1u << (c - 1);
-  // segments: enough threads to fill the machine, but keep >= 16 entries per segment on average
-  uint64_t entries = (uint64_t)n * cfg.W;
-  uint32_t nb = cfg.nbuckets();
-  uint64_t avg = entries / nb;
-  int want = (int)((148ull * 768 + nb - 1) / nb);
-  int cap = (int)(avg / 16);
-  int S = want < cap ? want : cap;
-  if (S < 1) S = 1;
-  if (S > 64) S = 64;
-  int env_s = env_int("ZKB200_SEGMENTS", 0);
-  if (env_s > 0) S = env_s;
-  cfg.S = S;
-  int L = precompute ? 8 : 16;
+  cfg.S = 1;
+  int L = 4;
   int env_l = env_int("ZKB200_REDUCE_CHUNK", 0);
   if (env_l > 0) L = env_l;
   while ((uint32_t)L > cfg.B) L >>= 1;
@@ -109,19 +111,51 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   cursor.alloc(nb);
   tile_sums.alloc(cdiv(nb, SCAN_TILE) + 1);
   entries.alloc((size_t)n * cfg.W);
-  parts.alloc((size_t)nb * cfg.S);
-  chunk_out.alloc((size_t)cfg.nwb * (cfg.B / cfg.L));
-  window_sums.alloc(cfg.nwb);
+  {
+    int per_sm = 0;
+    acc_variant = env_int("ZKB200_ACC_VARIANT", sizeof(F) > 48 ? 0 : ZK_ACC_VARIANT_DEFAULT);
+    switch (acc_variant) {
+      case 1: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, false>, 128, 0)); break;
+      case 2: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, true>, 128, 0)); break;
+      case 3: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 5, false>, 128, 0)); break;
+      default: acc_variant = 0; ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 3, true>, 128, 0));
+    }
+    if (per_sm < 1) per_sm = 1;
+    acc_blocks = (uint32_t)per_sm * (uint32_t)sm_count();
+  }
+  uint32_t cpw = cfg.B / cfg.L;
+  heavy.alloc((size_t)acc_blocks * 128 / 4 + 2);
+  for (int b = 0; b < 2; b++) {
+    bucket_sums[b].alloc(nb);
+    partial[b].alloc(2 * (size_t)acc_blocks * 128);
+    chunk_out[b].alloc((size_t)cfg.nwb * cpw);
+    tree_tmp[b].alloc((size_t)cfg.nwb * cdiv(cpw, 128) + 1);
+    window_sums[b].alloc(cfg.nwb + 1);
+  }
+  if (!tail) {
+    int lo = 0, hi = 0;
+    ZK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ZK_CUDA(cudaStreamCreateWithPriority(&tail, cudaStreamNonBlocking, hi));
+    for (int b = 0; b < 2; b++) {
+      ZK_CUDA(cudaEventCreateWithFlags(&ev_acc[b], cudaEventDisableTiming));
+      ZK_CUDA(cudaEventCreateWithFlags(&ev_tail[b], cudaEventDisableTiming));
+    }
+  }
+  pipelined = env_int("ZKB200_PIPELINE", 0) != 0;
 }
 
 template <class T>
-void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, cudaStream_t st) {
+void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes,
+                       cudaStream_t st) {
   ZK_REQUIRE(count > 0 && count <= n, ZK_EARG, "scalar count exceeds the base table");
   const uint32_t nb = cfg.nbuckets();
+  const int b = (int)(seq++ & 1);
   if (profile && !ev[0])
     for (auto& e : ev) ZK_CUDA(cudaEventCreate(&e));
-  auto mark = [&](int i) { if (profile) ZK_CUDA(cudaEventRecord(ev[i], st)); };
-  mark(0);
+  auto mark = [&](int i, cudaStream_t s) { if (profile) ZK_CUDA(cudaEventRecord(ev[i], s)); };
+  // ---- caller's stream: sort and accumulate ------------------------------------------------
+  if (tail_pending[b]) ZK_CUDA(cudaStreamWaitEvent(st, ev_tail[b], 0));   // parts[b] is free again
+  mark(0, st);
   ZK_CUDA(cudaMemsetAsync(counts.p, 0, nb * sizeof(uint32_t), st));
   k_digits<false><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, counts.p, nullptr);
   uint32_t ntiles = cdiv(nb, SCAN_TILE);
@@ -129,17 +163,56 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   k_scan_spine<<<1, 1024, 0, st>>>(tile_sums.p, ntiles);
   k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p, offsets.p, cursor.p);
   k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, cursor.p, entries.p);
-  mark(1);
-  uint32_t nthreads = nb * cfg.S;
-  k_accumulate<F><<<cdiv(nthreads, 128), 128, 0, st>>>(pts.p, entries.p, offsets.p, parts.p, nb, cfg.S);
-  mark(2);
+  mark(1, st);
+  switch (acc_variant) {
+    case 1: k_accumulate<F, 4, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
+    case 2: k_accumulate<F, 4, true><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
+    case 3: k_accumulate<F, 5, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
+    default: k_accumulate<F, 3, true><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb);
+  }
+  // (reads `offsets`, which the next MSM's scan overwrites: keep it on the caller's stream)
+  ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));
+  k_fix_partials<F><<<cdiv(nb, 128), 128, 0, st>>>(offsets.p, bucket_sums[b].p, partial[b].p, nb, acc_blocks * 128,
+                                                      heavy.p, heavy.p + 1);
+  k_fix_heavy<F><<<sm_count(), 128, 128 * sizeof(XYZZ<F>), st>>>(offsets.p, bucket_sums[b].p, partial[b].p, nb,
+                                                                   acc_blocks * 128, heavy.p, heavy.p + 1);
+  mark(2, st);
+  ZK_CUDA(cudaEventRecord(ev_acc[b], st));
+  // ---- side stream: the latency-bound tail ---------------------------------------------------
+  ZK_CUDA(cudaStreamWaitEvent(tail, ev_acc[b], 0));
   uint32_t cpw = cfg.B / cfg.L;
-  k_reduce_chunks<F><<<cdiv((size_t)cpw * cfg.nwb, 128), 128, 0, st>>>(parts.p, cfg, chunk_out.p);
-  k_reduce_tree<F><<<cfg.nwb, 128, 128 * sizeof(XYZZ<F>), st>>>(chunk_out.p, cpw, window_sums.p);
-  mark(3);
-  k_horner<F><<<1, 32, 0, st>>>(window_sums.p, cfg, d_result);
-  mark(4);
+  k_reduce_chunks<F><<<cdiv((size_t)cpw * cfg.nwb, 128), 128, 0, tail>>>(bucket_sums[b].p, cfg, chunk_out[b].p);
+  {
+    // sum tree: cpw -> ceil(cpw / 128) -> ... -> 1 per window
+    const XYZZ<F>* src = chunk_out[b].p;
+    uint32_t cnt = cpw;
+    XYZZ<F>* bufs[2] = {tree_tmp[b].p, chunk_out[b].p};   // ping-pong (chunk_out is dead after level 1)
+    int which = 0;
+    while (true) {
+      uint32_t blocks = cdiv(cnt, 128);
+      XYZZ<F>* dst = blocks == 1 ? window_sums[b].p : bufs[which];
+      k_reduce_tree<F><<<dim3(blocks, cfg.nwb), 128, 128 * sizeof(XYZZ<F>), tail>>>(src, cnt, dst);
+      if (blocks == 1) break;
+      src = dst;
+      cnt = blocks;
+      which ^= 1;
+    }
+  }
+  mark(3, tail);
+  XYZZ<F>* res = d_result ? d_result : window_sums[b].p + cfg.nwb;
+  k_horner<F><<<1, 32, 0, tail>>>(window_sums[b].p, cfg, res);
+  if (d_out_bytes) finalize_points<T>(res, 1, d_out_bytes, tail);
+  mark(4, tail);
+  ZK_CUDA(cudaEventRecord(ev_tail[b], tail));
+  tail_pending[b] = true;
   ZK_CUDA(cudaGetLastError());
+  if (!pipelined) join(st);
+}
+
+template <class T>
+void BaseTable<T>::join(cudaStream_t st) {
+  for (int b = 0; b < 2; b++)
+    if (tail_pending[b]) ZK_CUDA(cudaStreamWaitEvent(st, ev_tail[b], 0));
 }
 
 template <class T>
@@ -154,12 +227,17 @@ template <class T>
 BaseTable<T>::~BaseTable() {
   for (auto& e : ev)
     if (e) cudaEventDestroy(e);
+  for (int b = 0; b < 2; b++) {
+    if (ev_acc[b]) cudaEventDestroy(ev_acc[b]);
+    if (ev_tail[b]) cudaEventDestroy(ev_tail[b]);
+  }
+  if (tail) cudaStreamDestroy(tail);
 }
 
 template <class T>
 size_t BaseTable<T>::device_bytes() const {
   return pts.bytes() + skip.bytes() + counts.bytes() + offsets.bytes() + cursor.bytes() + tile_sums.bytes() +
-         entries.bytes() + parts.bytes() + chunk_out.bytes() + window_sums.bytes();
+         entries.bytes() + heavy.bytes() + 2 * (bucket_sums[0].bytes() + partial[0].bytes() + chunk_out[0].bytes() + tree_tmp[0].bytes() + window_sums[0].bytes());
 }
 
 template <class T>

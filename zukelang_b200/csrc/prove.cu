@@ -151,12 +151,13 @@ static void groth16_finish(zk::Groth16Key* k, zk::QapDevice& q, cudaStream_t st,
   uint32_t span = std::max(std::max(L.ti_cnt, L.h_cnt), std::max(L.mid_cnt, 1u));
   k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, q.Vc.p, q.H.p, k->d_sol.p, k->mid_index.p, k->d_rs.p, k->sA.p,
                                                       k->qB.scalars.p, k->qC.scalars.p);
-  k->qC.table.run(k->sA.p, 3 + L.ti_cnt, k->r1.p + 0, st);             // A
-  k->qC.table.run(k->qC.scalars.p, k->qC.table.n, k->r1.p + 1, st);     // C
-  k->qB.table.run(k->qB.scalars.p, k->qB.table.n, k->r2.p, st);         // B
-  finalize_points<G1Traits>(k->r1.p + 0, 1, k->d_out.p, st);
-  finalize_points<G2Traits>(k->r2.p, 1, k->d_out.p + ZK_G1_OUT, st);
-  finalize_points<G1Traits>(k->r1.p + 1, 1, k->d_out.p + ZK_G1_OUT + ZK_G2_OUT, st);
+  // tails (bucket reduction, affine conversion) of A and C overlap the next accumulation
+  k->qC.table.pipelined = k->qB.table.pipelined = true;
+  k->qC.table.run(k->sA.p, 3 + L.ti_cnt, nullptr, k->d_out.p, st);                                           // A
+  k->qC.table.run(k->qC.scalars.p, k->qC.table.n, nullptr, k->d_out.p + ZK_G1_OUT + ZK_G2_OUT, st);         // C
+  k->qB.table.run(k->qB.scalars.p, k->qB.table.n, nullptr, k->d_out.p + ZK_G1_OUT, st);                     // B
+  k->qC.table.join(st);
+  k->qB.table.join(st);
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_GROTH16_PROOF_OUT, cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
@@ -381,20 +382,13 @@ int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* s
                                                         k->q_vv.scalars.p, k->q_ww.scalars.p, k->q_yy.scalars.p,
                                                         k->q_vav.scalars.p, k->q_waw.scalars.p, k->q_yay.scalars.p,
                                                         k->q_bvwy.scalars.p, k->q_h.scalars.p);
-  auto run1 = [&](Query<G1Traits>& qq, int slot) { qq.table.run(qq.scalars.p, qq.table.n, k->r1.p + slot, st); };
-  auto run2 = [&](Query<G2Traits>& qq, int slot) { qq.table.run(qq.scalars.p, qq.table.n, k->r2.p + slot, st); };
-  run1(k->q_vv, 0); run1(k->q_yy, 1); run1(k->q_h, 2); run1(k->q_vav, 3); run1(k->q_yay, 4); run1(k->q_bvwy, 5);
-  run2(k->q_ww, 0); run2(k->q_waw, 1);
-  // output order: vv ww yy h vavv waww yayy bvwy
+  // output order: vv ww yy h vavv waww yayy bvwy; every query's tail overlaps the next accumulation
   uint8_t* o = k->d_out.p;
-  finalize_points<G1Traits>(k->r1.p + 0, 1, o, st); o += ZK_G1_OUT;
-  finalize_points<G2Traits>(k->r2.p + 0, 1, o, st); o += ZK_G2_OUT;
-  finalize_points<G1Traits>(k->r1.p + 1, 1, o, st); o += ZK_G1_OUT;
-  finalize_points<G1Traits>(k->r1.p + 2, 1, o, st); o += ZK_G1_OUT;
-  finalize_points<G1Traits>(k->r1.p + 3, 1, o, st); o += ZK_G1_OUT;
-  finalize_points<G2Traits>(k->r2.p + 1, 1, o, st); o += ZK_G2_OUT;
-  finalize_points<G1Traits>(k->r1.p + 4, 1, o, st); o += ZK_G1_OUT;
-  finalize_points<G1Traits>(k->r1.p + 5, 1, o, st);
+  auto run1 = [&](Query<G1Traits>& qq) { qq.table.pipelined = true; qq.table.run(qq.scalars.p, qq.table.n, nullptr, o, st); o += ZK_G1_OUT; };
+  auto run2 = [&](Query<G2Traits>& qq) { qq.table.pipelined = true; qq.table.run(qq.scalars.p, qq.table.n, nullptr, o, st); o += ZK_G2_OUT; };
+  run1(k->q_vv); run2(k->q_ww); run1(k->q_yy); run1(k->q_h); run1(k->q_vav); run2(k->q_waw); run1(k->q_yay); run1(k->q_bvwy);
+  k->q_vv.table.join(st); k->q_ww.table.join(st); k->q_yy.table.join(st); k->q_h.table.join(st);
+  k->q_vav.table.join(st); k->q_waw.table.join(st); k->q_yay.table.join(st); k->q_bvwy.table.join(st);
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_PINOCCHIO_PROOF_OUT, cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
