@@ -223,3 +223,59 @@ def test_curve_mirror_semantics(zk):
     assert G1.to_compressed_bytes(G1.one) == O.G1_GEN_COMPRESSED
     assert C.G2.to_compressed_bytes(C.G2.one) == O.G2_GEN_COMPRESSED
     assert C.G2.add(C.G2.of_Fr(2), C.G2.of_Fr(3)) == C.G2.of_Fr(5)
+
+
+@pytest.mark.parametrize("shards", [2, 3])
+def test_sharded_prove_equals_unsharded(zk, shards):
+    """key handles loaded as shard i of N return partial sums whose sum is the proof
+    (N emulated in one process; the N > 1 transport is covered by tests/test_cpu_dist.py)."""
+    import ctypes
+    from zukelang_b200 import _lib, dist as D, groth16 as G16, pinocchio as PN
+    from zukelang_b200.curve import Fr, fr_vector
+    circ, wit = Z.circuit_mulchain(21)
+    oq = Z.qap_build(circ.gates)
+    q = H.mirror_qap(oq)
+    sol = wit(12345)
+    keys = q.variables()
+    # Groth16
+    whole = G16.Make()
+    pk, _ = whole.keygen(random.Random(3), H.mirror_circuit(circ), q)
+    r, s = 1111, 2222
+    ref = whole.prove_with(r, s, q, pk, sol)
+    parts = []
+    for i in range(shards):
+        P = G16.Make(shard=(i, shards))
+        out = (ctypes.c_uint8 * _lib.GROTH16_PROOF_OUT)()
+        _lib.check(zk.zk_groth16_prove(P._key_handle(pk, q), q.handle(), fr_vector(sol[k] for k in keys),
+                                       Fr.to_bytes(r), Fr.to_bytes(s), out))
+        parts.append(bytes(out))
+    comb = D.combine_groth16(parts)
+    assert comb[96:144] + comb[336:432] + comb[528:576] == ref.to_compressed_bytes()
+    G16.Make.free(pk)
+    # Pinocchio ZK
+    circ2, wit2 = Z.circuit_pair_case(10)
+    oq2 = Z.qap_build(circ2.gates)
+    q2 = H.mirror_qap(oq2)
+    sol2 = wit2(5)
+    keys2 = q2.variables()
+    M = PN.Make()
+    pk2, _ = M.ZK.keygen(random.Random(8), H.mirror_circuit(circ2), q2)
+    d = (31, 41, 59)
+    ref2 = M.ZK.prove_with(d, q2, pk2, sol2)
+    parts2 = []
+    for i in range(shards):
+        S = PN.ZK(shard=(i, shards))
+        out = (ctypes.c_uint8 * _lib.PINOCCHIO_PROOF_OUT)()
+        _lib.check(zk.zk_pinocchio_prove(S._key_handle(pk2, q2), q2.handle(), fr_vector(sol2[k] for k in keys2),
+                                         fr_vector(d), out))
+        parts2.append(bytes(out))
+    comb2 = D.combine_pinocchio(parts2)
+    got, o = b"", 0
+    for is2 in PN.PROOF_IS_G2:
+        raw, comp = (192, 96) if is2 else (96, 48)
+        got += comb2[o + raw:o + raw + comp]
+        o += raw + comp
+    assert got == ref2.to_compressed_bytes()
+    M.ZK.free(pk2)
+    q.free()
+    q2.free()
