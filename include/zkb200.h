@@ -138,6 +138,7 @@ typedef struct {
   size_t n;                  /* degree of target = number of gates */
   size_t m;                  /* number of variables = witness length */
   size_t n_mid;              /* |Dom(ltd_mid)| */
+  size_t n_h;                /* points in tiztd; 0 means n - 1 (the reference's length) */
   const uint32_t *mid_index; /* n_mid entries */
   const uint8_t *a, *b1, *d1;   /* G1: alpha, beta, delta            (ZK_G1_RAW each) */
   const uint8_t *b2, *d2;       /* G2: beta, delta                   (ZK_G2_RAW each) */
@@ -161,6 +162,21 @@ int zk_groth16_prove(uint64_t pk, uint64_t qap, const uint8_t *sol, const uint8_
  * zk_quotient_domain_load handle.  Used when the dense QAP.t cannot exist. */
 int zk_groth16_prove_coeffs(uint64_t pk, uint64_t qap, const uint8_t *vwy, const uint8_t *sol,
                             const uint8_t r[32], const uint8_t s[32], uint8_t proof_out[ZK_GROTH16_PROOF_OUT]);
+
+/* ---- evaluation-form Groth16 for circuits too large for a dense QAP.t ----
+ * The QAP polynomials are handled by their values on the reference's own domain 0..n-1
+ * (QAP.ml:84) and h by its values on n..2n-1; the key given to zk_groth16_pk_load then holds the
+ * Lagrange-basis points ti1 = [L_j(tau)]1, ti2 = [L_j(tau)]2, tiztd = [L'_k(tau) Z(tau)/delta]1
+ * (n_h = n) derived at key generation.  Proof elements are the same group elements as
+ * zk_groth16_prove's.
+ * zk_eval_domain_load: w = barycentric weights 1 / prod_{i != j} (j - i), t_shift[k] = t(n + k).
+ * zk_r1cs_load: CSR matrix `which` (0 = Gate.l, 1 = Gate.r, 2 = Gate.lhs; circuit.ml:75) with n
+ * rows and m columns (variables in increasing Var order).  Handles are freed with zk_qap_free. */
+int zk_eval_domain_load(size_t n, const uint8_t *w, const uint8_t *t_shift, uint64_t *handle);
+int zk_r1cs_load(uint64_t domain, int which, size_t m, const uint32_t *row_ptr, const uint32_t *col,
+                 const uint8_t *val);
+int zk_groth16_prove_r1cs(uint64_t pk, uint64_t domain, const uint8_t *sol, const uint8_t r[32],
+                          const uint8_t s[32], uint8_t proof_out[ZK_GROTH16_PROOF_OUT]);
 
 /* ---- Pinocchio (Protocol 2) --------------------------------------------------------------
  * The proving key of /root/reference/src/pinocchio/pinocchio.ml:37-60, flattened as above.

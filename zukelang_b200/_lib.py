@@ -63,6 +63,9 @@ SIGNATURES = {
     "zk_groth16_pk_load": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64)]),
     "zk_groth16_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zk_groth16_prove_coeffs": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zk_eval_domain_load": (c_int, [c_size_t, c_void_p, c_void_p, POINTER(c_uint64)]),
+    "zk_r1cs_load": (c_int, [c_uint64, c_int, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "zk_groth16_prove_r1cs": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zk_pinocchio_pk_load": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64)]),
     "zk_pinocchio_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),
     "zk_key_free": (c_int, [c_uint64]),
@@ -72,7 +75,7 @@ SIGNATURES = {
 
 class Groth16PKeyStruct(ctypes.Structure):
     """zk_groth16_pkey of include/zkb200.h."""
-    _fields_ = [("n", c_size_t), ("m", c_size_t), ("n_mid", c_size_t), ("mid_index", c_void_p),
+    _fields_ = [("n", c_size_t), ("m", c_size_t), ("n_mid", c_size_t), ("n_h", c_size_t), ("mid_index", c_void_p),
                 ("a", c_void_p), ("b1", c_void_p), ("d1", c_void_p), ("b2", c_void_p), ("d2", c_void_p),
                 ("ti1", c_void_p), ("ti2", c_void_p), ("tiztd", c_void_p), ("ltd_mid", c_void_p)]
 

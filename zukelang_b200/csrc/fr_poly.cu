@@ -272,6 +272,152 @@ static int log2_ceil_u32(uint32_t n) {
   return l;
 }
 
+// ---------------------------------------------------------------------------
+// EvalDomain (evaluation-form quotient)
+// ---------------------------------------------------------------------------
+// out[which][j] = sum over row j of val * sol[col]   (blockIdx.y = matrix)
+struct CsrPtrs {
+  const uint32_t* row_ptr[3];
+  const uint32_t* col[3];
+  const Fr* val[3];
+};
+static __global__ void __launch_bounds__(128)
+k_csr_matvec(CsrPtrs m, const Fr* __restrict__ sol, uint32_t n, Fr* __restrict__ out) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int which = blockIdx.y;
+  const uint32_t* rp = m.row_ptr[which];
+  Fr acc = Fr::zero();
+  for (uint32_t k = rp[j]; k < rp[j + 1]; k++) acc = acc + load_vec(&m.val[which][k]) * load_vec(&sol[m.col[which][k]]);
+  store_vec(&out[(size_t)which * n + j], acc);
+}
+// gate check V(j) W(j) == Y(j) and a = w .* evals zero-padded to D (3 vectors)
+static __global__ void __launch_bounds__(128)
+k_eval_prepare(const Fr* __restrict__ evals, const Fr* __restrict__ w, uint32_t n, uint32_t D, Fr* __restrict__ work,
+               int* flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  Fr a[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
+  if (i < n) {
+    Fr wi = load_vec(&w[i]);
+    Fr v = load_vec_rw(&evals[i]), ww = load_vec_rw(&evals[(size_t)n + i]), y = load_vec_rw(&evals[2 * (size_t)n + i]);
+    if (v * ww != y) atomicExch(flag, 1);
+    a[0] = v * wi; a[1] = ww * wi; a[2] = y * wi;
+  }
+  for (int q = 0; q < 3; q++) store_vec(&work[(size_t)q * D + i], a[q]);
+}
+static __global__ void k_mul_by_ghat(Fr* __restrict__ work, const Fr* __restrict__ ghat, uint32_t D) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  Fr g = load_vec(&ghat[i]);
+  for (int q = 0; q < 3; q++) store_vec(&work[(size_t)q * D + i], load_vec_rw(&work[(size_t)q * D + i]) * g);
+}
+// H[k] = c1[k] * SV[n+k] * SW[n+k] - c2 * SY[n+k]
+static __global__ void k_eval_quotient(const Fr* __restrict__ work, const Fr* __restrict__ c1, const Fr* __restrict__ c2,
+                                       uint32_t n, uint32_t D, Fr* __restrict__ H) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Fr sv = load_vec_rw(&work[n + k]), sw = load_vec_rw(&work[(size_t)D + n + k]), sy = load_vec_rw(&work[2 * (size_t)D + n + k]);
+  store_vec(&H[k], load_vec(&c1[k]) * sv * sw - load_vec_rw(c2) * sy);
+}
+// kernel 1/d: g[0] = 0, g[i] = to_mont(i) (inverted afterwards), zero beyond 2n
+static __global__ void k_fill_index(Fr* __restrict__ g, uint32_t limit, uint32_t D) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  Fr a = Fr::zero();
+  if (i >= 1 && i < limit) { a.v[0] = i; a = a.to_mont(); } else a = Fr::one();   // placeholders inverted to 1
+  store_vec(&g[i], a);
+}
+static __global__ void k_clear_outside(Fr* __restrict__ g, uint32_t limit, uint32_t D) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  if (i == 0 || i >= limit) store_vec(&g[i], Fr::zero());
+}
+// c1[k] = t_shift[k] * dinv^2
+static __global__ void k_scale_c1(Fr* __restrict__ c1, const Fr* __restrict__ dinv, uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Fr d = load_vec_rw(dinv);
+  store_vec(&c1[k], load_vec_rw(&c1[k]) * d * d);
+}
+
+void EvalDomain::load(uint32_t n_, const uint8_t* w_raw, const uint8_t* t_shift_raw, cudaStream_t st) {
+  ZK_REQUIRE(n_ >= 2 && n_ < (1u << 26), ZK_EARG, "eval_domain_load: bad size");
+  n = n_;
+  int logD = 1;
+  while ((1ull << logD) < 2ull * n) logD++;
+  plan.build(logD, st);
+  const uint32_t D = plan.D;
+  flag.alloc(2);
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
+  w.alloc(n); c1.alloc(n); c2.alloc(1); ghat.alloc(D);
+  {
+    DevBuf<uint32_t> raw((size_t)n * 8);
+    ZK_CUDA(cudaMemcpyAsync(raw.p, w_raw, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    fr_to_mont(raw.p, w.p, n, flag.p, st);
+    ZK_CUDA(cudaMemcpyAsync(raw.p, t_shift_raw, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    fr_to_mont(raw.p, c1.p, n, flag.p, st);
+    ZK_CUDA(cudaStreamSynchronize(st));
+  }
+  {
+    DevBuf<Fr> consts(5);
+    k_ntt_consts<<<1, 1, 0, st>>>(logD, consts.p);
+    ZK_CUDA(cudaMemcpyAsync(c2.p, consts.p + 4, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    k_scale_c1<<<cdiv(n, 256), 256, 0, st>>>(c1.p, c2.p, n);
+    ZK_CUDA(cudaStreamSynchronize(st));
+  }
+  k_fill_index<<<cdiv(D, 256), 256, 0, st>>>(ghat.p, 2 * n, D);
+  k_fr_batch_inverse<<<cdiv(cdiv(D, 16), 64), 64, 0, st>>>(ghat.p, D, flag.p + 1);
+  k_clear_outside<<<cdiv(D, 256), 256, 0, st>>>(ghat.p, 2 * n, D);
+  plan.forward(ghat.p, st);
+  evals.alloc(3 * (size_t)n);
+  work.alloc(3 * (size_t)D);
+  H.alloc(n);
+  int fl[2];
+  ZK_CUDA(cudaMemcpyAsync(fl, flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "eval_domain_load: scalar is not canonical (>= r)");
+}
+
+void EvalDomain::load_matrix(int which, uint32_t m_, const uint32_t* row_ptr, const uint32_t* col, const uint8_t* val_raw,
+                             cudaStream_t st) {
+  ZK_REQUIRE(which >= 0 && which < 3 && row_ptr && m_ > 0, ZK_EARG, "r1cs_load: bad arguments");
+  ZK_REQUIRE(m == 0 || m == m_, ZK_EARG, "r1cs_load: matrices disagree on the number of variables");
+  m = m_;
+  uint32_t nnz = row_ptr[n];
+  for (uint32_t j = 0; j < n; j++) ZK_REQUIRE(row_ptr[j] <= row_ptr[j + 1], ZK_EARG, "r1cs_load: row_ptr not monotone");
+  for (uint32_t k = 0; k < nnz; k++) ZK_REQUIRE(col[k] < m, ZK_EARG, "r1cs_load: column index out of range");
+  SparseMat& M = mat[which];
+  M.row_ptr.alloc(n + 1);
+  M.col.alloc(nnz ? nnz : 1);
+  M.val.alloc(nnz ? nnz : 1);
+  ZK_CUDA(cudaMemcpyAsync(M.row_ptr.p, row_ptr, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (nnz) {
+    DevBuf<uint32_t> raw((size_t)nnz * 8);
+    ZK_CUDA(cudaMemcpyAsync(M.col.p, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    ZK_CUDA(cudaMemcpyAsync(raw.p, val_raw, (size_t)nnz * 32, cudaMemcpyHostToDevice, st));
+    fr_to_mont(raw.p, M.val.p, nnz, flag.p, st);
+    ZK_CUDA(cudaStreamSynchronize(st));
+  }
+  sol_m.ensure(m);
+}
+
+void EvalDomain::eval(const uint32_t* d_sol_raw, cudaStream_t st) {
+  const uint32_t D = plan.D;
+  ZK_REQUIRE(mat[0].row_ptr.p && mat[1].row_ptr.p && mat[2].row_ptr.p, ZK_EARG, "prove_r1cs: matrices not loaded");
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
+  fr_to_mont(d_sol_raw, sol_m.p, m, flag.p, st);
+  CsrPtrs P;
+  for (int q = 0; q < 3; q++) { P.row_ptr[q] = mat[q].row_ptr.p; P.col[q] = mat[q].col.p; P.val[q] = mat[q].val.p; }
+  k_csr_matvec<<<dim3(cdiv(n, 128), 3), 128, 0, st>>>(P, sol_m.p, n, evals.p);
+  k_eval_prepare<<<cdiv(D, 128), 128, 0, st>>>(evals.p, w.p, n, D, work.p, flag.p + 1);
+  ntt_forward_batch(plan, work.p, 3, st);
+  k_mul_by_ghat<<<cdiv(D, 256), 256, 0, st>>>(work.p, ghat.p, D);
+  ntt_inverse_batch(plan, work.p, 3, st);
+  k_eval_quotient<<<cdiv(n, 256), 256, 0, st>>>(work.p, c1.p, c2.p, n, D, H.p);
+  ZK_CUDA(cudaGetLastError());
+}
+
 struct QuotientScratch {
   DevBuf<Fr> work;  // 3 * D
 };
@@ -382,8 +528,27 @@ int zk_quotient_domain_load(const uint8_t* target, size_t n, uint64_t* handle) {
 int zk_qap_free(uint64_t handle) {
   ZK_API_BEGIN
   ZK_CUDA(cudaDeviceSynchronize());
-  zk::lookup_handle(handle, 3);
+  zk::HandleBase* h = zk::lookup_handle(handle, 0);
+  ZK_REQUIRE(h->kind == 3 || h->kind == 6, ZK_EARG, "qap_free: not a QAP / domain handle");
   zk::drop_handle(handle);
+  ZK_API_END
+}
+
+int zk_eval_domain_load(size_t n, const uint8_t* w, const uint8_t* t_shift, uint64_t* handle) {
+  ZK_API_BEGIN
+  using namespace zk;
+  ZK_REQUIRE(w && t_shift && handle, ZK_EARG, "eval_domain_load: null argument");
+  auto h = std::make_unique<EvalDomainHandle>();
+  h->d.load((uint32_t)n, w, t_shift, default_stream());
+  *handle = register_handle(std::move(h));
+  ZK_API_END
+}
+
+int zk_r1cs_load(uint64_t domain, int which, size_t m, const uint32_t* row_ptr, const uint32_t* col, const uint8_t* val) {
+  ZK_API_BEGIN
+  using namespace zk;
+  auto* h = static_cast<EvalDomainHandle*>(lookup_handle(domain, 6));
+  h->d.load_matrix(which, (uint32_t)m, row_ptr, col, val, default_stream());
   ZK_API_END
 }
 

@@ -52,6 +52,41 @@ struct QapDevice {
   void quotient_from_work(cudaStream_t st);
 };
 
+// Evaluation-form quotient for circuits whose dense QAP.t cannot exist.
+// The QAP polynomials are handled by their values on the reference's own domain 0..n-1
+// (QAP.ml:84): V(j) = <gate_j.l, sol> is a sparse mat-vec, and h = (V W - Y) / t, of degree
+// <= n - 2, is represented by its values at the n shifted points u_k = n + k:
+//     V(u_k) = t(u_k) * sum_j w_j V(j) / (u_k - j),   w_j = 1 / prod_{i != j} (j - i)
+// i.e. one cyclic convolution (size D >= 2n) of w .* V with the kernel 1/d, so that
+//     h(u_k) = t(u_k) * SV_k * SW_k - SY_k.
+// The matching proving key holds the Lagrange-basis points [L_j(tau)]G and
+// [L'_k(tau) Z(tau) / delta]G instead of the monomial ones; the proof elements are the same
+// group elements as the reference's (tests compare the bytes of both paths).
+struct SparseMat {                 // CSR over Fr: n rows (gates) x m columns (variables)
+  DevBuf<uint32_t> row_ptr, col;
+  DevBuf<Fr> val;                  // Montgomery
+};
+struct EvalDomain {
+  uint32_t n = 0, m = 0;
+  NttPlan plan;                    // cyclic NTT of size D >= 2n
+  DevBuf<Fr> w;                    // barycentric weights on 0..n-1
+  DevBuf<Fr> c1;                   // t(u_k) / D^2
+  DevBuf<Fr> c2;                   // 1 / D   (one element)
+  DevBuf<Fr> ghat;                 // NTT of the kernel 1/d, bit-reversed
+  SparseMat mat[3];                // l, r, lhs coefficient matrices (Gate.l / .r / .lhs, circuit.ml:75)
+  DevBuf<Fr> sol_m, evals, work, H;  // witness; V|W|Y on the domain (3n); 3D scratch; h(u_k) (n)
+  DevBuf<int> flag;                // [0] non-canonical input, [1] V(j) W(j) != Y(j) for some gate
+  void load(uint32_t n, const uint8_t* w_raw, const uint8_t* t_shift_raw, cudaStream_t st);
+  void load_matrix(int which, uint32_t m, const uint32_t* row_ptr, const uint32_t* col, const uint8_t* val_raw,
+                   cudaStream_t st);
+  // d_sol_raw: m canonical scalars.  Fills evals and H; sets flag[1] if a gate is violated.
+  void eval(const uint32_t* d_sol_raw, cudaStream_t st);
+};
+struct EvalDomainHandle : HandleBase {
+  EvalDomain d;
+  EvalDomainHandle() { kind = 6; }
+};
+
 struct QapHandle : HandleBase {
   QapDevice q;
   DevBuf<uint32_t> d_raw;   // staging for host-facing calls

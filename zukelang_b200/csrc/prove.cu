@@ -120,7 +120,7 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
   k->m = (uint32_t)pk->m;
   k->n_mid = (uint32_t)pk->n_mid;
   slice(pk->n, shard_index, shard_count, &L.ti_lo, &L.ti_cnt);
-  slice(pk->n - 1, shard_index, shard_count, &L.h_lo, &L.h_cnt);
+  slice(pk->n_h ? pk->n_h : pk->n - 1, shard_index, shard_count, &L.h_lo, &L.h_cnt);
   slice(pk->n_mid, shard_index, shard_count, &L.mid_lo, &L.mid_cnt);
   L.singles = shard_index == 0;
   std::vector<uint8_t> t1, t2;
@@ -145,11 +145,11 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
   ZK_API_END
 }
 
-static void groth16_finish(zk::Groth16Key* k, zk::QapDevice& q, cudaStream_t st, uint8_t* proof_out) {
+static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* flag, cudaStream_t st, uint8_t* proof_out) {
   using namespace zk;
   const G16Layout& L = k->lay;
   uint32_t span = std::max(std::max(L.ti_cnt, L.h_cnt), std::max(L.mid_cnt, 1u));
-  k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, q.Vc.p, q.H.p, k->d_sol.p, k->mid_index.p, k->d_rs.p, k->sA.p,
+  k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, vwy, Hq, k->d_sol.p, k->mid_index.p, k->d_rs.p, k->sA.p,
                                                       k->qB.scalars.p, k->qC.scalars.p);
   // tails (bucket reduction, affine conversion) of A and C overlap the next accumulation
   k->qC.table.pipelined = k->qB.table.pipelined = true;
@@ -160,7 +160,7 @@ static void groth16_finish(zk::Groth16Key* k, zk::QapDevice& q, cudaStream_t st,
   k->qB.table.join(st);
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_GROTH16_PROOF_OUT, cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(fl, flag, sizeof(fl), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaStreamSynchronize(st));
   ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "groth16_prove: scalar is not canonical (>= r)");
   ZK_REQUIRE(fl[1] == 0, ZK_EREMAINDER, "groth16_prove: V*W - Y is not divisible by the target (QAP.ml:134)");
@@ -194,7 +194,7 @@ int zk_groth16_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* sol
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
   q.eval(k->d_sol.p, st);
-  groth16_finish(k, q, st, proof_out);
+  groth16_finish(k, q.Vc.p, q.H.p, q.flag.p, st, proof_out);
   ZK_API_END
 }
 
@@ -218,7 +218,29 @@ int zk_groth16_prove_coeffs(uint64_t pk_handle, uint64_t qap_handle, const uint8
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
   q.set_coeffs(qh->d_raw.p, st);
   q.quotient_from_work(st);
-  groth16_finish(k, q, st, proof_out);
+  groth16_finish(k, q.Vc.p, q.H.p, q.flag.p, st, proof_out);
+  ZK_API_END
+}
+
+// Evaluation-form prover for large circuits: `pk` holds the Lagrange-basis derived key (ti1 = [L_j(tau)]1,
+// ti2 = [L_j(tau)]2, tiztd = [L'_k(tau) Z(tau)/delta]1 with n_h = n), `domain` the evaluation domain
+// with the circuit's sparse matrices.  Same proof elements as zk_groth16_prove on the dense QAP.
+int zk_groth16_prove_r1cs(uint64_t pk_handle, uint64_t domain_handle, const uint8_t* sol, const uint8_t* r,
+                          const uint8_t* s, uint8_t* proof_out) {
+  ZK_API_BEGIN
+  using namespace zk;
+  auto* k = static_cast<Groth16Key*>(lookup_handle(pk_handle, 4));
+  auto* dh = static_cast<EvalDomainHandle*>(lookup_handle(domain_handle, 6));
+  EvalDomain& d = dh->d;
+  ZK_REQUIRE(sol && r && s && proof_out, ZK_EARG, "groth16_prove_r1cs: null argument");
+  ZK_REQUIRE(d.n == k->lay.n && d.m == k->m, ZK_EARG, "groth16_prove_r1cs: key and domain dimensions differ");
+  check_rs(r, s);
+  cudaStream_t st = default_stream();
+  ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
+  d.eval(k->d_sol.p, st);
+  groth16_finish(k, d.evals.p, d.H.p, d.flag.p, st, proof_out);
   ZK_API_END
 }
 
