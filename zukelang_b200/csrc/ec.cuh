@@ -14,6 +14,14 @@
 typedef Mont<FpParams> Fp;
 typedef Mont<FrParams> Fr;
 
+// The one out-of-line Fp product: arguments and result stay in registers under the device ABI.
+// Used by Fp2 and FpCall, where fully inlined formulas would be tens of kilobytes of code.
+#ifndef ZK_HOST_SIM
+static __device__ __noinline__ Fp fp_mul_outofline(Fp a, Fp b) { return a * b; }
+#else
+static inline Fp fp_mul_outofline(Fp a, Fp b) { return a * b; }
+#endif
+
 // -------------------------------------------------------------------------
 // Fp2 = Fp[u] / (u^2 + 1)
 // -------------------------------------------------------------------------
@@ -30,17 +38,17 @@ struct Fp2 {
   ZK_HD Fp2 dbl() const { return Fp2{c0.dbl(), c1.dbl()}; }
   // Karatsuba: 3 Fp products
   friend ZK_HD Fp2 operator*(const Fp2& a, const Fp2& b) {
-    Fp t0 = Fp::mul_call(a.c0, b.c0);
-    Fp t1 = Fp::mul_call(a.c1, b.c1);
-    Fp t2 = Fp::mul_call(a.c0 + a.c1, b.c0 + b.c1);
+    Fp t0 = fp_mul_outofline(a.c0, b.c0);
+    Fp t1 = fp_mul_outofline(a.c1, b.c1);
+    Fp t2 = fp_mul_outofline(a.c0 + a.c1, b.c0 + b.c1);
     return Fp2{t0 - t1, t2 - t0 - t1};
   }
   // (c0 + c1 u)^2 = (c0 + c1)(c0 - c1) + 2 c0 c1 u : 2 Fp products
   ZK_HD Fp2 sqr() const {
     Fp s = c0 + c1;
     Fp d = c0 - c1;
-    Fp m = Fp::mul_call(c0, c1);
-    return Fp2{Fp::mul_call(s, d), m.dbl()};
+    Fp m = fp_mul_outofline(c0, c1);
+    return Fp2{fp_mul_outofline(s, d), m.dbl()};
   }
   ZK_NI Fp2 inverse() const {
     Fp n = Fp::mul_call(c0, c0) + Fp::mul_call(c1, c1);
@@ -52,9 +60,6 @@ struct Fp2 {
 // Fp with the product routed through ONE out-of-line routine (arguments and result stay in
 // registers under the device ABI).  Same representation as Fp; used where the fully inlined
 // point formulas would overflow the instruction cache.
-#ifndef ZK_HOST_SIM
-static __device__ __noinline__ Fp fp_mul_outofline(Fp a, Fp b) { return a * b; }
-#endif
 struct FpCall {
   Fp f;
   static ZK_HD FpCall zero() { return FpCall{Fp::zero()}; }

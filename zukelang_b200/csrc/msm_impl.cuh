@@ -113,8 +113,10 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   entries.alloc((size_t)n * cfg.W);
   {
     int per_sm = 0;
-    acc_variant = env_int("ZKB200_ACC_VARIANT", sizeof(F) > 48 ? 0 : ZK_ACC_VARIANT_DEFAULT);
+    acc_variant = env_int(sizeof(F) > 48 ? "ZKB200_ACC_VARIANT_G2" : "ZKB200_ACC_VARIANT", sizeof(F) > 48 ? 4 : ZK_ACC_VARIANT_DEFAULT);
     switch (acc_variant) {
+      case 4: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); break;
+      case 5: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 1, false>, 128, 0)); break;
       case 1: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, false>, 128, 0)); break;
       case 2: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, true>, 128, 0)); break;
       case 3: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 5, false>, 128, 0)); break;
@@ -165,6 +167,8 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, cursor.p, entries.p);
   mark(1, st);
   switch (acc_variant) {
+    case 4: k_accumulate<F, 2, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
+    case 5: k_accumulate<F, 1, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
     case 1: k_accumulate<F, 4, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
     case 2: k_accumulate<F, 4, true><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
     case 3: k_accumulate<F, 5, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
