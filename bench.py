@@ -222,30 +222,34 @@ def run_gpu_arm(args):
         tot = sum(a * d for a, d in zip(ints, dl_all)) % R
         host = torch.from_numpy(np.ascontiguousarray(w[lo:hi]).view(np.int64)).pin_memory()
         batches.append({"host": host, "dev": host.cuda(), "expect_dlog": tot})
-    d_out = torch.zeros(144, dtype=torch.uint8, device="cuda")
-    d_ring = torch.zeros(pool, 144, dtype=torch.uint8, device="cuda")     # one result slot per batch
+    QUEUE = 8                                           # zk_table_pipeline batches up to 8 tails
+    d_ring = torch.zeros(QUEUE, 144, dtype=torch.uint8, device="cuda")    # one result slot per queued MSM
+    p_ring = torch.zeros(QUEUE, 96, dtype=torch.uint8, device="cuda")     # partial sums to gather (N > 1)
+    g_ring = torch.zeros(world, QUEUE, 96, dtype=torch.uint8, device="cuda")
+    s_ring = torch.zeros(QUEUE, 144, dtype=torch.uint8, device="cuda")
     side = torch.cuda.Stream()
-    gathered = torch.zeros(world * 96, dtype=torch.uint8, device="cuda")
-    d_sum = torch.zeros(144, dtype=torch.uint8, device="cuda")
+    pipelined = not args.no_pipeline
 
-    def reduce_shards():
-        """N > 1: all-gather the 96-byte partial sums over NCCL and add them on every rank"""
-        dist.all_gather_into_tensor(gathered, d_out[:96].contiguous())
-        _lib.check(zk.zk_g1_sum_dev(gathered.data_ptr(), world, d_sum.data_ptr(), side.cuda_stream))
-        return d_sum
-
-    def step_device(b):
-        """one MSM with device-resident scalars; returns the result tensor (on device).
-        N = 1: consecutive steps are pipelined (zk_table_pipeline): the tail of step i overlaps the
-        accumulation of step i+1 and results are valid after zk_table_join."""
-        if world == 1:
-            _lib.check(zk.zk_g1_table_msm_dev(handle.value, batches[b]["dev"].data_ptr(), n, d_ring[b].data_ptr(), side.cuda_stream))
-            return d_ring[b]
-        _lib.check(zk.zk_g1_table_msm_dev(handle.value, batches[b]["dev"].data_ptr(), n, d_out.data_ptr(), side.cuda_stream))
-        return reduce_shards()
-
-    def join():
-        _lib.check(zk.zk_table_join(handle.value, side.cuda_stream))
+    def run_steps(batch_ids):
+        """One MSM per entry of batch_ids, device-resident scalars, on stream `side`.
+        Pipelined: groups of up to 8 MSMs sort + accumulate back to back, then ONE batched tail
+        (zk_table_join) finishes the group; for N > 1 the group's partial sums travel in one
+        all_gather and are added by one batched kernel.  Returns the last result tensor."""
+        group = QUEUE if pipelined else 1
+        last = None
+        for g0 in range(0, len(batch_ids), group):
+            ids = batch_ids[g0:g0 + group]
+            for q, b in enumerate(ids):
+                _lib.check(zk.zk_g1_table_msm_dev(handle.value, batches[b]["dev"].data_ptr(), n, d_ring[q].data_ptr(),
+                                                  side.cuda_stream))
+            _lib.check(zk.zk_table_join(handle.value, side.cuda_stream))
+            last = d_ring[len(ids) - 1]
+            if world > 1:
+                p_ring.copy_(d_ring[:, :96])
+                dist.all_gather_into_tensor(g_ring.view(-1), p_ring.view(-1))
+                _lib.check(zk.zk_g1_sum_strided_dev(g_ring.data_ptr(), world, QUEUE, s_ring.data_ptr(), side.cuda_stream))
+                last = s_ring[len(ids) - 1]
+        return last
 
     def combine(res):
         return bytes(res.cpu().numpy())[:96]
@@ -271,44 +275,37 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     # ---- warm-up, with the exact known-dlog check -------------------------------------------
+    _lib.check(zk.zk_table_pipeline(handle.value, 1 if pipelined else 0))
     with torch.cuda.stream(side):
         for it in range(args.warmup):
             b = it % pool
-            parts = step_device(b)
-            join()
+            res = run_steps([b])
             side.synchronize()
-            got = combine(parts)
-            assert got == expected_point(batches[b]["expect_dlog"]), "MSM result differs from the known-dlog closed form"
+            assert combine(res) == expected_point(batches[b]["expect_dlog"]), "MSM result differs from the known-dlog closed form"
 
     # ---- timed region: `value` (inputs resident in HBM) -----------------------------------------
-    _lib.check(zk.zk_table_profile(handle.value, 1, None))
-    if world == 1 and not args.no_pipeline:
-        _lib.check(zk.zk_table_pipeline(handle.value, 1))
-    acc_ms, stage = [], (ctypes.c_float * 4)()
+    stage = (ctypes.c_float * 4)()
+    slots = [(args.warmup + it) % pool for it in range(args.steps)]   # scalar batch of every step
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(side):
         e0.record(side)
-        for it in range(args.steps):
-            parts = step_device((args.warmup + it) % pool)
-        join()
+        res = run_steps(slots)
         e1.record(side)
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    _lib.check(zk.zk_table_profile(handle.value, 1, stage))     # stages of the last timed step
-    acc_last_ms = float(stage[1])
-    stages_last = [float(x) for x in stage]
     clocks = sampler.stop()
-    final = combine(parts)
-    assert final == expected_point(batches[(args.warmup + args.steps - 1) % pool]["expect_dlog"])
-    # per-step accumulate time over a few more profiled steps (events are per step)
+    assert combine(res) == expected_point(batches[slots[-1]]["expect_dlog"])
+    # stage times of the dominant kernel: a few more steps, one at a time, with stage events on
+    acc_ms, stages_last = [], None
+    _lib.check(zk.zk_table_profile(handle.value, 1, None))
     with torch.cuda.stream(side):
         for it in range(min(args.steps, 5)):
-            step_device(it % pool)
-            join()
+            run_steps([it % pool])
             side.synchronize()
             _lib.check(zk.zk_table_profile(handle.value, 1, stage))
             acc_ms.append(float(stage[1]))
+            stages_last = [float(x) for x in stage]
     _lib.check(zk.zk_table_profile(handle.value, 0, None))
     _lib.check(zk.zk_table_pipeline(handle.value, 0))
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -326,9 +323,10 @@ def run_gpu_arm(args):
             b = (args.warmup + it) % pool
             _lib.check(zk.zk_g1_table_msm(handle.value, batches[b]["host"].data_ptr(), n, out_host.data_ptr()))
             if world > 1:
-                d_out.copy_(out_host, non_blocking=True)
-                res = reduce_shards()
-                out_host.copy_(res)
+                p_ring[0].copy_(out_host[:96], non_blocking=True)
+                dist.all_gather_into_tensor(g_ring.view(-1), p_ring.view(-1))
+                _lib.check(zk.zk_g1_sum_strided_dev(g_ring.data_ptr(), world, QUEUE, s_ring.data_ptr(), side.cuda_stream))
+                out_host.copy_(s_ring[0])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -357,13 +355,13 @@ def run_gpu_arm(args):
                        "points": n_total, "points_per_gpu": n, "window_bits": c, "windows": W,
                        "precomputed_table": bool(info[7]), "table_MiB_per_gpu": int(info[5]) >> 20,
                        "segments": int(info[4]), "true_mixed_adds_per_point": W,
-                       "pipelined_steps": bool(world == 1 and not args.no_pipeline),
+                       "pipelined_steps": bool(pipelined),
                        "l2": "inputs larger than L2 (table %d MiB, %d rotating scalar batches of %d MiB)" % (int(info[5]) >> 20, pool, (n * 32) >> 20),
-                       "parallelism": "base-range shards x%d, all_gather of 96-B partial sums" % world, "setup_s": setup_s},
+                       "parallelism": "base-range shards x%d, all_gather of 96-B partial sums (one per group of %d steps)" % (world, QUEUE if pipelined else 1), "setup_s": setup_s},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 144,
                     "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": (13 if world == 1 else 15) * args.steps,
+            "gpu_launches": 14 * args.steps,
             "roofline": {"bound": "int32-imad", "kernel": "k_accumulate<Fp>", "achieved": achieved,
                          "peak": peak_mac32 / 1e12, "unit": "TMAC32/s", "frac": achieved / (peak_mac32 / 1e12),
                          "traffic": None, "kernel_ms": acc_avg, "stages_ms_last_step": stages_last,

@@ -81,11 +81,12 @@ int zk_g2_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *
  * [4] = segments, [5] = device bytes, [6] = points, [7] = precomputed */
 int zk_table_info(uint64_t handle, uint64_t info[8]);
 /* Pipelining of consecutive *_msm_dev calls on one table.  Each MSM ends in a latency-bound
- * tail (bucket reduction, window combine, affine conversion) that runs on the table's own
- * high-priority side stream.  With enable = 0 (default) a call makes cuda_stream wait for that
- * tail, i.e. plain stream order.  With enable != 0 the call returns once the tail is enqueued, so
- * the next MSM's sort + accumulation overlaps it; d_out of every outstanding call is valid on
- * cuda_stream only after zk_table_join(handle, cuda_stream). */
+ * tail (bucket reduction, window combine, affine conversion: ~40 dependent point operations) whose
+ * wall time is the same for one MSM as for a batch.  With enable = 0 (default) every call runs its
+ * own tail: plain stream order.  With enable != 0 a call only sorts and accumulates into one of 8
+ * bucket buffers and queues its tail; zk_table_join(handle, cuda_stream) (or the 9th call) runs
+ * ONE batched tail for everything queued.  d_out of a queued call is valid on cuda_stream after
+ * the join. */
 int zk_table_pipeline(uint64_t handle, int enable);
 int zk_table_join(uint64_t handle, void *cuda_stream);
 /* Stage timing for the roofline leg of bench.py: enable != 0 makes the following MSMs on this
@@ -102,6 +103,10 @@ int zk_g1_sum(const uint8_t *points, size_t k, uint8_t out[ZK_G1_OUT]);
 int zk_g2_sum(const uint8_t *points, size_t k, uint8_t out[ZK_G2_OUT]);
 int zk_g1_sum_dev(const void *d_points, size_t k, void *d_out, void *cuda_stream);
 int zk_g2_sum_dev(const void *d_points, size_t k, void *d_out, void *cuda_stream);
+/* Batched form for one gather of `batch` queued results from k shards: d_points is laid out
+ * [shard][batch] (what all_gather_into_tensor produces), out[q] = sum over shards of point q. */
+int zk_g1_sum_strided_dev(const void *d_points, size_t k, size_t batch, void *d_out, void *cuda_stream);
+int zk_g2_sum_strided_dev(const void *d_points, size_t k, size_t batch, void *d_out, void *cuda_stream);
 
 /* ---- fixed-base batch: out[i] = scalars[i] * generator -------------------------
  * Replaces Curve.G.of_Fr (curve.ml:180) / powers (:106-109) when applied to a vector.

@@ -53,6 +53,8 @@ SIGNATURES = {
     "zk_g2_sum": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_g1_sum_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_g2_sum_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "zk_g1_sum_strided_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "zk_g2_sum_strided_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "zk_g1_fixed_base_mul": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_g2_fixed_base_mul": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_qap_load": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, POINTER(c_uint64)]),

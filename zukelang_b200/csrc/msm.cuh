@@ -327,12 +327,17 @@ __device__ __noinline__ XYZZ<F> small_mul(const XYZZ<F>& p, uint32_t k) {
 
 // Step 5a: thread (window wb, chunk ch) reduces L consecutive buckets with the running-sum
 // trick:  V = sum_{j<L} (ch*L + j + 1) * bucket[ch*L + j].
+// (tail kernels use 64-thread blocks so that they fit in the registers a pipelined accumulation
+// leaves free on every SM)
+constexpr int TAIL_THREADS = 64;
 template <class F>
-__global__ void __launch_bounds__(128)
-k_reduce_chunks(const XYZZ<F>* __restrict__ bucket_sums, MsmConfig cfg, XYZZ<F>* __restrict__ chunk_out) {
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_reduce_chunks(const XYZZ<F>* __restrict__ bucket_sums_all, MsmConfig cfg, XYZZ<F>* __restrict__ chunk_out_all) {
   uint32_t chunks_per_window = cfg.B / cfg.L;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= chunks_per_window * (uint32_t)cfg.nwb) return;
+  const XYZZ<F>* bucket_sums = bucket_sums_all + (size_t)blockIdx.z * cfg.nbuckets();       // z = queued MSM
+  XYZZ<F>* chunk_out = chunk_out_all + (size_t)blockIdx.z * chunks_per_window * cfg.nwb;
   uint32_t wb = t / chunks_per_window, ch = t % chunks_per_window;
   uint32_t first = wb * cfg.B + ch * cfg.L;
   XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
@@ -347,14 +352,16 @@ k_reduce_chunks(const XYZZ<F>* __restrict__ bucket_sums, MsmConfig cfg, XYZZ<F>*
   store_vec(&chunk_out[t], acc);
 }
 
-// Step 5b: one level of the sum tree: block (x, window y) adds up to 128 consecutive elements of
-// its window (count per window = n_in) and writes one: out[y * gridDim.x + x].
+// Step 5b: one level of the sum tree: block (x, window y, queued MSM z) adds up to TAIL_THREADS
+// consecutive elements of its window (count per window = n_in) and writes one:
+// out[z * out_stride + y * gridDim.x + x].
 template <class F>
-__global__ void __launch_bounds__(128)
-k_reduce_tree(const XYZZ<F>* __restrict__ in, uint32_t n_in, XYZZ<F>* __restrict__ out) {
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_reduce_tree(const XYZZ<F>* __restrict__ in, uint32_t n_in, size_t in_stride, XYZZ<F>* __restrict__ out,
+              size_t out_stride) {
   extern __shared__ uint4 smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  const XYZZ<F>* src = in + (size_t)blockIdx.y * n_in;
+  const XYZZ<F>* src = in + (size_t)blockIdx.z * in_stride + (size_t)blockIdx.y * n_in;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   XYZZ<F> acc = XYZZ<F>::inf();
   if (i < n_in) acc = load_vec_rw(&src[i]);
@@ -368,23 +375,40 @@ k_reduce_tree(const XYZZ<F>* __restrict__ in, uint32_t n_in, XYZZ<F>* __restrict
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) store_vec(&out[(size_t)blockIdx.y * gridDim.x + blockIdx.x], sm[0]);
+  if (threadIdx.x == 0) store_vec(&out[(size_t)blockIdx.z * out_stride + (size_t)blockIdx.y * gridDim.x + blockIdx.x], sm[0]);
 }
 
-// Step 6: result = sum_w 2^(c*w) * window_sums[w]   (Horner; nwb == 1 just copies)
+// Output slots of the queued MSMs (passed by value to the batched tail kernels).
+constexpr int MSM_QUEUE = 8;
 template <class F>
-__global__ void k_horner(const XYZZ<F>* __restrict__ window_sums, MsmConfig cfg, XYZZ<F>* __restrict__ result) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+struct TailOutputs {
+  XYZZ<F>* result[MSM_QUEUE];   // XYZZ sum (always set: caller's slot or table scratch)
+  uint8_t* bytes[MSM_QUEUE];    // RAW + COMP wire bytes, nullable
+};
+
+// Step 6 + 7 for every queued MSM (block z): result = sum_w 2^(c*w) * window_sums[w] (Horner; a copy
+// when the table is precomputed), then XYZZ -> affine -> wire bytes.
+template <class T>
+__global__ void k_combine_finalize(const XYZZ<typename T::F>* __restrict__ window_sums_all, MsmConfig cfg,
+                                   TailOutputs<typename T::F> outs) {
+  typedef typename T::F F;
+  if (threadIdx.x != 0) return;
+  const int z = blockIdx.x;
+  const XYZZ<F>* window_sums = window_sums_all + (size_t)z * (cfg.nwb + 1);
   XYZZ<F> acc = load_vec_rw(&window_sums[cfg.nwb - 1]);
   for (int w = cfg.nwb - 2; w >= 0; w--) {
     for (int i = 0; i < cfg.c; i++) acc = acc.dbl();
     XYZZ<F> p = load_vec_rw(&window_sums[w]);
     acc.add(p);
   }
-  store_vec(result, acc);
+  store_vec(outs.result[z], acc);
+  if (outs.bytes[z]) {
+    Affine<F> a = acc.to_affine();
+    T::serialize(a, outs.bytes[z]);
+  }
 }
 
-// Step 7: `count` XYZZ results -> RAW + COMP bytes each
+// `count` XYZZ results -> RAW + COMP bytes each
 template <class T>
 __global__ void k_finalize(const XYZZ<typename T::F>* __restrict__ results, int count, uint8_t* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -480,17 +504,16 @@ struct BaseTable {
   DevBuf<uint8_t> skip;      // 1 = identity base
   // workspace (reused by every MSM on this table; calls on one table are stream-ordered)
   DevBuf<uint32_t> counts, offsets, cursor, tile_sums, entries, heavy;   // heavy[0] = queue length, then the queue
-  // Bucket sums and the reduction scratch are double-buffered: the latency-bound tail of MSM i
-  // (bucket reduction, window combine, affine conversion) runs on `tail`, a high-priority side
-  // stream, while the caller's stream already sorts and accumulates MSM i+1.
-  DevBuf<XYZZ<F>> bucket_sums[2], partial[2], chunk_out[2], tree_tmp[2], window_sums[2];
+  // Deferred tails.  The latency-bound end of an MSM (bucket reduction, window combine, affine
+  // conversion: ~40 dependent point operations) costs the same wall time for one MSM as for a batch,
+  // so a pipelined table queues up to MSM_QUEUE accumulated MSMs (one bucket_sums slot each) and
+  // finishes them with ONE batched launch sequence on the caller's stream (flush / join).
+  DevBuf<XYZZ<F>> bucket_sums, partial, chunk_out, tree_tmp, window_sums;   // MSM_QUEUE slots each (partial: 1)
   uint32_t acc_blocks = 0;   // persistent grid of k_accumulate: resident blocks per SM x SMs
   int acc_variant = 0;       // 0: 3 blocks/SM + prefetch, 1: 4 no prefetch, 2: 4 + prefetch, 3: 5 no prefetch
-  cudaStream_t tail = nullptr;
-  cudaEvent_t ev_acc[2] = {nullptr, nullptr}, ev_tail[2] = {nullptr, nullptr};
-  bool tail_pending[2] = {false, false};
-  uint64_t seq = 0;
-  bool pipelined = false;   // false: run() joins the tail before returning (plain stream order)
+  int queued = 0;
+  TailOutputs<F> outs{};
+  bool pipelined = false;    // false: every run() flushes immediately (plain stream order)
 
   static MsmConfig choose_config(uint32_t n, bool precompute, int force_c);
   void load(const uint8_t* host_raw, const uint8_t* host_inf, uint32_t n, bool precompute, int force_c,
@@ -500,11 +523,11 @@ struct BaseTable {
   // d_scalars: count * 32 B canonical little-endian; uses bases [0, count).
   // d_result (nullable) receives the XYZZ sum, d_out_bytes (nullable) the RAW + COMP bytes.
   void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes, cudaStream_t st);
-  // make `st` wait for every outstanding tail of this table
+  // finish every queued MSM on `st` (batched tail); results are valid in stream order afterwards
   void join(cudaStream_t st);
   // stage timing (bench.py's roofline leg): when `profile` is set, run() brackets its stages with
   // CUDA events; stage_ms() reads them after the streams have drained.
-  // stages: 0 digits+scan+scatter, 1 accumulate, 2 bucket reduce (incl. wait), 3 combine+finalize
+  // stages: 0 digits+scan+scatter, 1 accumulate (+ partial fix-up), 2 bucket reduce, 3 combine+finalize
   bool profile = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void stage_ms(float out[4]);

@@ -100,6 +100,31 @@ __global__ void k_sum_raw(const uint8_t* __restrict__ raw, uint32_t k, XYZZ<type
   store_vec(out, acc);
 }
 
+// batched form for the shard gather: out[q] = sum_r points[r * batch + q], one block per q
+template <class T>
+__global__ void k_sum_strided(const uint8_t* __restrict__ raw, uint32_t k, uint32_t batch, uint8_t* __restrict__ out) {
+  if (threadIdx.x) return;
+  const uint32_t q = blockIdx.x;
+  XYZZ<typename T::F> acc = XYZZ<typename T::F>::inf();
+  for (uint32_t r = 0; r < k; r++) {
+    Affine<typename T::F> p;
+    if (T::parse(raw + ((size_t)r * batch + q) * T::RAW, p)) continue;
+    acc.madd(p);
+  }
+  Affine<typename T::F> a = acc.to_affine();
+  T::serialize(a, out + (size_t)q * (T::RAW + T::COMP));
+}
+
+template <class T>
+int api_sum_strided_dev(const void* d_points, size_t k, size_t batch, void* d_out, void* stream) {
+  ZK_API_BEGIN
+  ZK_REQUIRE(d_points && d_out && k > 0 && k <= 4096 && batch > 0 && batch <= 65535, ZK_EARG, "sum_strided_dev: bad arguments");
+  cudaStream_t st = stream ? (cudaStream_t)stream : default_stream();
+  k_sum_strided<T><<<(unsigned)batch, 32, 0, st>>>((const uint8_t*)d_points, (uint32_t)k, (uint32_t)batch, (uint8_t*)d_out);
+  ZK_CUDA(cudaGetLastError());
+  ZK_API_END
+}
+
 template <class T>
 int api_sum_dev(const void* d_points, size_t k, void* d_out, void* stream) {
   ZK_API_BEGIN

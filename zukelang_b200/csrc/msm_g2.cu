@@ -28,4 +28,7 @@ int zk_g2_sum(const uint8_t* points, size_t k, uint8_t* out) { return zk::api_su
 int zk_g2_sum_dev(const void* d_points, size_t k, void* d_out, void* stream) {
   return zk::api_sum_dev<G2Traits>(d_points, k, d_out, stream);
 }
+int zk_g2_sum_strided_dev(const void* d_points, size_t k, size_t batch, void* d_out, void* stream) {
+  return zk::api_sum_strided_dev<G2Traits>(d_points, k, batch, d_out, stream);
+}
 }

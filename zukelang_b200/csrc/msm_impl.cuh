@@ -127,22 +127,12 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   }
   uint32_t cpw = cfg.B / cfg.L;
   heavy.alloc((size_t)acc_blocks * 128 / 4 + 2);
-  for (int b = 0; b < 2; b++) {
-    bucket_sums[b].alloc(nb);
-    partial[b].alloc(2 * (size_t)acc_blocks * 128);
-    chunk_out[b].alloc((size_t)cfg.nwb * cpw);
-    tree_tmp[b].alloc((size_t)cfg.nwb * cdiv(cpw, 128) + 1);
-    window_sums[b].alloc(cfg.nwb + 1);
-  }
-  if (!tail) {
-    int lo = 0, hi = 0;
-    ZK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    ZK_CUDA(cudaStreamCreateWithPriority(&tail, cudaStreamNonBlocking, hi));
-    for (int b = 0; b < 2; b++) {
-      ZK_CUDA(cudaEventCreateWithFlags(&ev_acc[b], cudaEventDisableTiming));
-      ZK_CUDA(cudaEventCreateWithFlags(&ev_tail[b], cudaEventDisableTiming));
-    }
-  }
+  partial.alloc(2 * (size_t)acc_blocks * 128);
+  bucket_sums.alloc((size_t)MSM_QUEUE * nb);
+  chunk_out.alloc((size_t)MSM_QUEUE * cfg.nwb * cpw);
+  tree_tmp.alloc((size_t)MSM_QUEUE * cfg.nwb * cdiv(cpw, TAIL_THREADS) + 1);
+  window_sums.alloc((size_t)MSM_QUEUE * (cfg.nwb + 1));
+  queued = 0;
   pipelined = env_int("ZKB200_PIPELINE", 0) != 0;
 }
 
@@ -151,13 +141,13 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
                        cudaStream_t st) {
   ZK_REQUIRE(count > 0 && count <= n, ZK_EARG, "scalar count exceeds the base table");
   const uint32_t nb = cfg.nbuckets();
-  const int b = (int)(seq++ & 1);
+  if (queued == MSM_QUEUE) join(st);
+  const int slot = queued;
   if (profile && !ev[0])
     for (auto& e : ev) ZK_CUDA(cudaEventCreate(&e));
-  auto mark = [&](int i, cudaStream_t s) { if (profile) ZK_CUDA(cudaEventRecord(ev[i], s)); };
-  // ---- caller's stream: sort and accumulate ------------------------------------------------
-  if (tail_pending[b]) ZK_CUDA(cudaStreamWaitEvent(st, ev_tail[b], 0));   // parts[b] is free again
-  mark(0, st);
+  auto mark = [&](int i) { if (profile) ZK_CUDA(cudaEventRecord(ev[i], st)); };
+  // ---- sort and accumulate -----------------------------------------------------------------
+  mark(0);
   ZK_CUDA(cudaMemsetAsync(counts.p, 0, nb * sizeof(uint32_t), st));
   k_digits<false><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, counts.p, nullptr);
   uint32_t ntiles = cdiv(nb, SCAN_TILE);
@@ -165,58 +155,65 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   k_scan_spine<<<1, 1024, 0, st>>>(tile_sums.p, ntiles);
   k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p, offsets.p, cursor.p);
   k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, cursor.p, entries.p);
-  mark(1, st);
+  mark(1);
+  XYZZ<F>* bsum = bucket_sums.p + (size_t)slot * nb;
+  const uint32_t grid = acc_blocks;
   switch (acc_variant) {
-    case 4: k_accumulate<F, 2, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
-    case 5: k_accumulate<F, 1, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
-    case 1: k_accumulate<F, 4, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
-    case 2: k_accumulate<F, 4, true><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
-    case 3: k_accumulate<F, 5, false><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb); break;
-    default: k_accumulate<F, 3, true><<<acc_blocks, 128, 0, st>>>(pts.p, entries.p, offsets.p, bucket_sums[b].p, partial[b].p, nb);
+    case 4: k_accumulate<F, 2, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
+    case 5: k_accumulate<F, 1, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
+    case 1: k_accumulate<F, 4, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
+    case 2: k_accumulate<F, 4, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
+    case 3: k_accumulate<F, 5, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
+    default: k_accumulate<F, 3, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb);
   }
-  // (reads `offsets`, which the next MSM's scan overwrites: keep it on the caller's stream)
   ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));
-  k_fix_partials<F><<<cdiv(nb, 128), 128, 0, st>>>(offsets.p, bucket_sums[b].p, partial[b].p, nb, acc_blocks * 128,
-                                                      heavy.p, heavy.p + 1);
-  k_fix_heavy<F><<<sm_count(), 128, 128 * sizeof(XYZZ<F>), st>>>(offsets.p, bucket_sums[b].p, partial[b].p, nb,
-                                                                   acc_blocks * 128, heavy.p, heavy.p + 1);
-  mark(2, st);
-  ZK_CUDA(cudaEventRecord(ev_acc[b], st));
-  // ---- side stream: the latency-bound tail ---------------------------------------------------
-  ZK_CUDA(cudaStreamWaitEvent(tail, ev_acc[b], 0));
-  uint32_t cpw = cfg.B / cfg.L;
-  k_reduce_chunks<F><<<cdiv((size_t)cpw * cfg.nwb, 128), 128, 0, tail>>>(bucket_sums[b].p, cfg, chunk_out[b].p);
-  {
-    // sum tree: cpw -> ceil(cpw / 128) -> ... -> 1 per window
-    const XYZZ<F>* src = chunk_out[b].p;
-    uint32_t cnt = cpw;
-    XYZZ<F>* bufs[2] = {tree_tmp[b].p, chunk_out[b].p};   // ping-pong (chunk_out is dead after level 1)
-    int which = 0;
-    while (true) {
-      uint32_t blocks = cdiv(cnt, 128);
-      XYZZ<F>* dst = blocks == 1 ? window_sums[b].p : bufs[which];
-      k_reduce_tree<F><<<dim3(blocks, cfg.nwb), 128, 128 * sizeof(XYZZ<F>), tail>>>(src, cnt, dst);
-      if (blocks == 1) break;
-      src = dst;
-      cnt = blocks;
-      which ^= 1;
-    }
-  }
-  mark(3, tail);
-  XYZZ<F>* res = d_result ? d_result : window_sums[b].p + cfg.nwb;
-  k_horner<F><<<1, 32, 0, tail>>>(window_sums[b].p, cfg, res);
-  if (d_out_bytes) finalize_points<T>(res, 1, d_out_bytes, tail);
-  mark(4, tail);
-  ZK_CUDA(cudaEventRecord(ev_tail[b], tail));
-  tail_pending[b] = true;
+  k_fix_partials<F><<<cdiv(nb, 128), 128, 0, st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p, heavy.p + 1);
+  k_fix_heavy<F><<<sm_count(), 128, 128 * sizeof(XYZZ<F>), st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p,
+                                                                   heavy.p + 1);
+  mark(2);
+  // ---- queue the tail ------------------------------------------------------------------------
+  outs.result[slot] = d_result ? d_result : window_sums.p + (size_t)slot * (cfg.nwb + 1) + cfg.nwb;
+  outs.bytes[slot] = d_out_bytes;
+  queued++;
   ZK_CUDA(cudaGetLastError());
   if (!pipelined) join(st);
 }
 
+// Batched tail of every queued MSM: bucket reduction, window combine, affine conversion.
 template <class T>
 void BaseTable<T>::join(cudaStream_t st) {
-  for (int b = 0; b < 2; b++)
-    if (tail_pending[b]) ZK_CUDA(cudaStreamWaitEvent(st, ev_tail[b], 0));
+  if (queued == 0) return;
+  const uint32_t nb = cfg.nbuckets();
+  const uint32_t cpw = cfg.B / cfg.L;
+  const int Q = queued;
+  k_reduce_chunks<F><<<dim3(cdiv((size_t)cpw * cfg.nwb, TAIL_THREADS), 1, Q), TAIL_THREADS, 0, st>>>(bucket_sums.p, cfg,
+                                                                                                     chunk_out.p);
+  {
+    // sum tree per (window, queued MSM): cpw -> ceil(cpw / TAIL_THREADS) -> ... -> 1
+    const XYZZ<F>* src = chunk_out.p;
+    size_t src_stride = (size_t)cfg.nwb * cpw;
+    uint32_t cnt = cpw;
+    XYZZ<F>* bufs[2] = {tree_tmp.p, chunk_out.p};   // ping-pong (chunk_out is dead after level 1)
+    size_t buf_stride[2] = {(size_t)cfg.nwb * cdiv(cpw, TAIL_THREADS), (size_t)cfg.nwb * cpw};
+    int which = 0;
+    while (true) {
+      uint32_t blocks = cdiv(cnt, TAIL_THREADS);
+      XYZZ<F>* dst = blocks == 1 ? window_sums.p : bufs[which];
+      size_t dst_stride = blocks == 1 ? (size_t)(cfg.nwb + 1) : buf_stride[which];
+      k_reduce_tree<F><<<dim3(blocks, cfg.nwb, Q), TAIL_THREADS, TAIL_THREADS * sizeof(XYZZ<F>), st>>>(src, cnt, src_stride,
+                                                                                                      dst, dst_stride);
+      if (blocks == 1) break;
+      src = dst;
+      src_stride = dst_stride;
+      cnt = blocks;
+      which ^= 1;
+    }
+  }
+  if (profile) ZK_CUDA(cudaEventRecord(ev[3], st));
+  k_combine_finalize<T><<<Q, 32, 0, st>>>(window_sums.p, cfg, outs);
+  if (profile) ZK_CUDA(cudaEventRecord(ev[4], st));
+  ZK_CUDA(cudaGetLastError());
+  queued = 0;
 }
 
 template <class T>
@@ -231,17 +228,12 @@ template <class T>
 BaseTable<T>::~BaseTable() {
   for (auto& e : ev)
     if (e) cudaEventDestroy(e);
-  for (int b = 0; b < 2; b++) {
-    if (ev_acc[b]) cudaEventDestroy(ev_acc[b]);
-    if (ev_tail[b]) cudaEventDestroy(ev_tail[b]);
-  }
-  if (tail) cudaStreamDestroy(tail);
 }
 
 template <class T>
 size_t BaseTable<T>::device_bytes() const {
   return pts.bytes() + skip.bytes() + counts.bytes() + offsets.bytes() + cursor.bytes() + tile_sums.bytes() +
-         entries.bytes() + heavy.bytes() + 2 * (bucket_sums[0].bytes() + partial[0].bytes() + chunk_out[0].bytes() + tree_tmp[0].bytes() + window_sums[0].bytes());
+         entries.bytes() + heavy.bytes() + bucket_sums.bytes() + partial.bytes() + chunk_out.bytes() + tree_tmp.bytes() + window_sums.bytes();
 }
 
 template <class T>
