@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 MAC32_PER_POINT = 48_000          # 16 windows x 3 000 MAC32 (G1 XYZZ mixed add)
 LOG_N = 20
+NCU_DRAM_BYTES_PER_LAUNCH = 3_128_247_616   # k_accumulate, 2^20 points, c = 17 (profiles/r01_ncu_accumulate.md)
 SEED_SCALARS, SEED_BASES = 0x5A554B45, 0x42415345
 
 
@@ -192,6 +193,9 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     os.environ.setdefault("ZKB200_DEVICE", str(local_rank))
     dist = None
+    # keep stdout to the single JSON line: NCCL's "NCCL version ..." banner goes to stdout
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
@@ -364,7 +368,8 @@ def run_gpu_arm(args):
             "gpu_launches": 14 * args.steps,
             "roofline": {"bound": "int32-imad", "kernel": "k_accumulate<Fp>", "achieved": achieved,
                          "peak": peak_mac32 / 1e12, "unit": "TMAC32/s", "frac": achieved / (peak_mac32 / 1e12),
-                         "traffic": None, "kernel_ms": acc_avg, "stages_ms_last_step": stages_last,
+                         "traffic": (NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.logn == 20 and c == 17) else None),
+                         "traffic_source": "profiles/r01_ncu_accumulate.md (ncu --set full, dram__bytes_read+write per launch)", "kernel_ms": acc_avg, "stages_ms_last_step": stages_last,
                          "algorithmic_mac32_per_point": MAC32_PER_POINT,
                          "peak_source": "mad.lo.cc/madc.hi.cc chains measured in this process (zk_bench_intpipe), /2",
                          "whole_step_frac": n_total / world * MAC32_PER_POINT / (dev_ms / args.steps * 1e-3) / peak_mac32,
@@ -372,6 +377,16 @@ def run_gpu_arm(args):
                                  "frac": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         }
+        if world == 1 and args.groth16_logn:
+            # second half of BASELINE.json's metric: Groth16 proofs/s on synthetic multiply-chain
+            # circuits (configs[2] at 2^16, configs[4] at 2^20), host witness in, proof bytes out,
+            # each proof checked against the closed-form trapdoor identity
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_groth16
+                line["groth16"] = [bench_groth16.run(zk, ln, 3, quiet=True) for ln in args.groth16_logn]
+            except Exception as e:                                 # never lose the headline line
+                line["groth16"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             sample = 1 << 14
@@ -396,6 +411,8 @@ def main():
     ap.add_argument("--logn", type=int, default=LOG_N)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--groth16-logn", type=int, nargs="*", default=[16],
+                    help="also time Groth16 prove at these constraint counts (N = 1 only)")
     ap.add_argument("--no-pipeline", action="store_true", help="plain stream order between steps")
     args = ap.parse_args()
     if args.warmup < 3:
