@@ -58,6 +58,29 @@ def uniform_scalars(n, seed):
 
 
 # ------------------------------------------------------------------------------------------
+# host placement
+# ------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs NVML reports as local to the GPU, BEFORE any pinned host memory
+    is allocated (first-touch places it on that NUMA node; a remote node costs ~4x H2D bandwidth)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %d-%d (%d)" % (min(cpus), max(cpus), len(cpus))
+    except Exception as e:
+        return "unchanged (%s)" % type(e).__name__
+    return "unchanged"
+
+
+# ------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -190,6 +213,7 @@ def run_gpu_arm(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+    affinity = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     os.environ.setdefault("ZKB200_DEVICE", str(local_rank))
     dist = None
@@ -319,20 +343,34 @@ def run_gpu_arm(args):
     value = n_total * args.steps / (dev_ms * 1e-3) / 1e6
 
     # ---- e2e: host buffers through the public C-ABI call (H2D + MSM + D2H per step) ---------------
-    out_host = torch.zeros(144, dtype=torch.uint8).pin_memory()
+    # context for e2e: this box's pinned host -> device bandwidth (e2e cannot beat n*32 B / this)
+    probe = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    dprobe = torch.empty_like(probe, device="cuda")
+    dprobe.copy_(probe, non_blocking=True)
+    torch.cuda.synchronize()
+    tp = time.perf_counter()
+    dprobe.copy_(probe, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = probe.numel() / (time.perf_counter() - tp) / 1e9
+    del probe, dprobe
+    # one call for all K steps: host scalar vectors in (pinned), K point results out; inside, the
+    # upload of step i+1 overlaps the accumulation of step i (zk_g1_table_msm_batch)
+    outs_host = torch.zeros(args.steps, 144, dtype=torch.uint8).pin_memory()
+    ptrs = (ctypes.c_void_p * args.steps)(*[batches[b]["host"].data_ptr() for b in slots])
     barrier()
     t0 = time.perf_counter()
-    with torch.cuda.stream(side):
-        for it in range(args.steps):
-            b = (args.warmup + it) % pool
-            _lib.check(zk.zk_g1_table_msm(handle.value, batches[b]["host"].data_ptr(), n, out_host.data_ptr()))
-            if world > 1:
-                p_ring[0].copy_(out_host[:96], non_blocking=True)
-                dist.all_gather_into_tensor(g_ring.view(-1), p_ring.view(-1))
-                _lib.check(zk.zk_g1_sum_strided_dev(g_ring.data_ptr(), world, QUEUE, s_ring.data_ptr(), side.cuda_stream))
-                out_host.copy_(s_ring[0])
+    _lib.check(zk.zk_g1_table_msm_batch(handle.value, ptrs, n, args.steps, outs_host.data_ptr()))
+    if world > 1:
+        with torch.cuda.stream(side):
+            parts = outs_host[:, :96].contiguous().cuda(non_blocking=True)
+            gathered = torch.empty(world, args.steps, 96, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(gathered.view(-1), parts.view(-1))
+            sums = torch.empty(args.steps, 144, dtype=torch.uint8, device="cuda")
+            _lib.check(zk.zk_g1_sum_strided_dev(gathered.data_ptr(), world, args.steps, sums.data_ptr(), side.cuda_stream))
+            outs_host.copy_(sums)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert bytes(outs_host[-1].numpy())[:96] == expected_point(batches[slots[-1]]["expect_dlog"]), "e2e result mismatch"
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -361,9 +399,11 @@ def run_gpu_arm(args):
                        "segments": int(info[4]), "true_mixed_adds_per_point": W,
                        "pipelined_steps": bool(pipelined),
                        "l2": "inputs larger than L2 (table %d MiB, %d rotating scalar batches of %d MiB)" % (int(info[5]) >> 20, pool, (n * 32) >> 20),
-                       "parallelism": "base-range shards x%d, all_gather of 96-B partial sums (one per group of %d steps)" % (world, QUEUE if pipelined else 1), "setup_s": setup_s},
+                       "parallelism": "base-range shards x%d, all_gather of 96-B partial sums (one per group of %d steps)" % (world, QUEUE if pipelined else 1), "setup_s": setup_s, "host_affinity": affinity},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 144,
+                    "api": "zk_g1_table_msm_batch: K host scalar vectors (pinned) in, K points out, uploads double-buffered",
+                    "h2d_gbs_measured": h2d_gbs, "h2d_bound_mpts": h2d_gbs * 1e9 / 32 / 1e6 * world,
                     "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": 14 * args.steps,
             "roofline": {"bound": "int32-imad", "kernel": "k_accumulate<Fp>", "achieved": achieved,

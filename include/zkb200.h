@@ -73,6 +73,12 @@ int zk_g2_table_load(const uint8_t *bases, const uint8_t *inf_flags, size_t n, i
 /* MSM of the first n table points with host scalars (copied in, result copied out). */
 int zk_g1_table_msm(uint64_t handle, const uint8_t *scalars, size_t n, uint8_t out[ZK_G1_OUT]);
 int zk_g2_table_msm(uint64_t handle, const uint8_t *scalars, size_t n, uint8_t out[ZK_G2_OUT]);
+/* `count` MSMs over the first n table points: scalars[i] points to the i-th host scalar vector,
+ * out receives count point results.  The uploads are double-buffered against the computation and
+ * the tails are batched, so a caller with many MSMs over one key (a stream of proofs) gets the
+ * device-resident rate end to end.  Pinned host memory makes the uploads asynchronous. */
+int zk_g1_table_msm_batch(uint64_t handle, const uint8_t *const *scalars, size_t n, size_t count, uint8_t *out);
+int zk_g2_table_msm_batch(uint64_t handle, const uint8_t *const *scalars, size_t n, size_t count, uint8_t *out);
 /* Same with device-resident scalars / result, enqueued on `cuda_stream` (a cudaStream_t,
  * NULL = the library stream) without synchronising. */
 int zk_g1_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *cuda_stream);

@@ -113,3 +113,42 @@ def test_table_msm_known_dlog(zk, gname, n, precompute):
         assert bytes(out) == expect(G.mul(G.one, sum(s * d for s, d in zip(ks, dl)) % R))
     finally:
         _lib.check(zk.zk_table_free(h.value))
+
+
+def test_table_msm_batch_and_pipelined_dev(zk):
+    """zk_g1_table_msm_batch (double-buffered uploads, batched tails) and the pipelined *_dev calls
+    give the same points as one-at-a-time calls; more MSMs than the tail queue holds."""
+    import numpy as np
+    import torch
+    from zukelang_b200 import _lib
+    n, count = 3000, 11
+    rng = random.Random(77)
+    dl = [rng.randrange(R) for _ in range(n)]
+    bases = (ctypes.c_uint8 * (96 * n))()
+    _lib.check(zk.zk_g1_fixed_base_mul(H.scalars_bytes(dl), n, bases))
+    h = ctypes.c_uint64()
+    _lib.check(zk.zk_g1_table_load(bases, None, n, 1, 0, ctypes.byref(h)))
+    try:
+        vecs, expect = [], []
+        for i in range(count):
+            ks = [rng.randrange(R) for _ in range(n)]
+            vecs.append(ctypes.create_string_buffer(H.scalars_bytes(ks), 32 * n))
+            expect.append(H.expect_g1(O.G1.mul(O.G1.one, sum(a * b for a, b in zip(ks, dl)) % R)))
+        ptrs = (ctypes.c_void_p * count)(*[ctypes.addressof(v) for v in vecs])
+        out = (ctypes.c_uint8 * (144 * count))()
+        _lib.check(zk.zk_g1_table_msm_batch(h.value, ptrs, n, count, out))
+        assert [bytes(out[i * 144:(i + 1) * 144]) for i in range(count)] == expect
+        # pipelined device calls + join
+        _lib.check(zk.zk_table_pipeline(h.value, 1))
+        d_sc = [torch.from_numpy(np.frombuffer(v.raw, dtype=np.uint8).copy()).cuda() for v in vecs]
+        d_out = torch.zeros(count, 144, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for i in range(count):
+                _lib.check(zk.zk_g1_table_msm_dev(h.value, d_sc[i].data_ptr(), n, d_out[i].data_ptr(), st.cuda_stream))
+            _lib.check(zk.zk_table_join(h.value, st.cuda_stream))
+        st.synchronize()
+        assert [bytes(d_out[i].cpu().numpy()) for i in range(count)] == expect
+        _lib.check(zk.zk_table_pipeline(h.value, 0))
+    finally:
+        _lib.check(zk.zk_table_free(h.value))

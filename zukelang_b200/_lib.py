@@ -42,6 +42,8 @@ SIGNATURES = {
     "zk_g2_table_load": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, POINTER(c_uint64)]),
     "zk_g1_table_msm": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p]),
     "zk_g2_table_msm": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p]),
+    "zk_g1_table_msm_batch": (c_int, [c_uint64, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "zk_g2_table_msm_batch": (c_int, [c_uint64, c_void_p, c_size_t, c_size_t, c_void_p]),
     "zk_g1_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_g2_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_table_info": (c_int, [c_uint64, POINTER(c_uint64)]),

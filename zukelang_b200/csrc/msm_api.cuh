@@ -57,6 +57,51 @@ int api_table_msm(uint64_t handle, const uint8_t* scalars, size_t n, uint8_t* ou
   ZK_API_END
 }
 
+// `count` MSMs over the same table with host scalars: uploads are double-buffered on a copy
+// stream so that H2D of MSM i+1 overlaps the accumulation of MSM i, tails are batched.
+template <class T>
+int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n, size_t count, uint8_t* out) {
+  ZK_API_BEGIN
+  auto* h = static_cast<TableHandle<T>*>(lookup_handle(handle, T::ID));
+  ZK_REQUIRE(scalars && out && count > 0 && n > 0 && n <= h->table.n, ZK_EARG, "msm_batch: bad arguments");
+  cudaStream_t st = default_stream();
+  static thread_local cudaStream_t cs = nullptr;
+  if (!cs) ZK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  DevBuf<uint32_t> d_sc[2];
+  d_sc[0].alloc(n * 8);
+  d_sc[1].alloc(n * 8);
+  DevBuf<uint8_t> d_outs(count * (T::RAW + T::COMP));
+  cudaEvent_t copied[2], consumed[2];
+  for (int b = 0; b < 2; b++) {
+    ZK_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+  }
+  ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st));
+  const bool was = h->table.pipelined;
+  h->table.pipelined = true;
+  for (size_t i = 0; i < count; i++) {
+    int b = (int)(i & 1);
+    ZK_REQUIRE(scalars[i], ZK_EARG, "msm_batch: null scalar vector");
+    if (i >= 2) ZK_CUDA(cudaStreamWaitEvent(cs, consumed[b], 0));
+    ZK_CUDA(cudaMemcpyAsync(d_sc[b].p, scalars[i], n * 32, cudaMemcpyHostToDevice, cs));
+    ZK_CUDA(cudaEventRecord(copied[b], cs));
+    ZK_CUDA(cudaStreamWaitEvent(st, copied[b], 0));
+    k_check_scalars<<<cdiv(n, 256), 256, 0, st>>>(d_sc[b].p, (uint32_t)n, h->d_err.p);
+    h->table.run(d_sc[b].p, (uint32_t)n, nullptr, d_outs.p + i * (T::RAW + T::COMP), st);
+    ZK_CUDA(cudaEventRecord(consumed[b], st));
+  }
+  h->table.join(st);
+  h->table.pipelined = was;
+  int err = 0;
+  ZK_CUDA(cudaMemcpyAsync(out, d_outs.p, count * (T::RAW + T::COMP), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_CUDA(cudaStreamSynchronize(cs));
+  for (int b = 0; b < 2; b++) { cudaEventDestroy(copied[b]); cudaEventDestroy(consumed[b]); }
+  ZK_REQUIRE(err == 0, ZK_EPOINT, "msm_batch: scalar is not canonical (>= r)");
+  ZK_API_END
+}
+
 template <class T>
 int api_table_msm_dev(uint64_t handle, const void* d_scalars, size_t n, void* d_out, void* stream) {
   ZK_API_BEGIN

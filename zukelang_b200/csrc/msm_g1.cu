@@ -38,4 +38,7 @@ int zk_g1_sum_dev(const void* d_points, size_t k, void* d_out, void* stream) {
 int zk_g1_sum_strided_dev(const void* d_points, size_t k, size_t batch, void* d_out, void* stream) {
   return zk::api_sum_strided_dev<G1Traits>(d_points, k, batch, d_out, stream);
 }
+int zk_g1_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n, size_t count, uint8_t* out) {
+  return zk::api_table_msm_batch<G1Traits>(handle, scalars, n, count, out);
+}
 }
