@@ -43,7 +43,7 @@ def microbench(zk):
         print(json.dumps({"probe": "intpipe", "kind": names[kind], "ops_per_s": best, "ms": ms.value}), flush=True)
 
 
-def msm_run(zk, group, logn, precompute, iters, c, seed=0x5A554B45):
+def msm_run(zk, group, logn, precompute, iters, c, seed=0x5A554B45, dist="uniform"):
     n = 1 << logn
     raw, outn = (96, 144) if group == "g1" else (192, 288)
     fixed = getattr(zk, "zk_%s_fixed_base_mul" % group)
@@ -61,6 +61,12 @@ def msm_run(zk, group, logn, precompute, iters, c, seed=0x5A554B45):
     info = (ctypes.c_uint64 * 8)()
     _lib.check(zk.zk_table_info(h.value, info))
     sc_w = rand_scalars(n, seed)
+    if dist == "witness":          # 90 % of the scalars in {0, 1}, 10 % uniform
+        rng = np.random.Generator(np.random.PCG64(seed + 1))
+        small = rng.random(n) < 0.9
+        bits = rng.integers(0, 2, size=n, dtype=np.uint64)
+        sc_w[small] = 0
+        sc_w[small, 0] = bits[small]
     d_sc = torch.from_numpy(sc_w.view(np.int64)).cuda()
     d_out = torch.zeros(outn, dtype=torch.uint8, device="cuda")
     side = torch.cuda.Stream()
@@ -86,7 +92,7 @@ def msm_run(zk, group, logn, precompute, iters, c, seed=0x5A554B45):
     ms = min(times)
     print(json.dumps({"probe": "msm", "group": group, "log_n": logn, "precompute": precompute, "c": int(info[0]),
                       "W": int(info[1]), "S": int(info[4]), "table_MB": int(info[5]) >> 20, "ms": ms,
-                      "ms_all": times, "Mpts_per_s": n / ms / 1e3, "exact_ok": bool(ok),
+                      "ms_all": times, "Mpts_per_s": n / ms / 1e3, "exact_ok": bool(ok), "scalars": dist,
                       "fixed_base_s": t_fixed, "load_s": t_load}), flush=True)
     return ok
 
@@ -99,6 +105,7 @@ def main():
     ap.add_argument("--precompute", type=int, nargs="*", default=[0, 1])
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--c", type=int, default=0)
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "witness"])
     args = ap.parse_args()
     zk = _lib.lib()
     info = ctypes.create_string_buffer(256)
@@ -109,7 +116,7 @@ def main():
     ok = True
     for logn in args.logn:
         for pre in args.precompute:
-            ok &= msm_run(zk, args.group, logn, pre, args.iters, args.c)
+            ok &= msm_run(zk, args.group, logn, pre, args.iters, args.c, dist=args.dist)
     sys.exit(0 if ok else 1)
 
 

@@ -56,14 +56,15 @@ __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* k, int pos, int 
 // a window for c = 17, 19, 20.  Digits d lie in [-(2^(c-1) - 1), 2^(c-1)] with a carry into the
 // next window; zero digits (and identity bases) emit nothing.
 // entry = point index (w * stride + i when precomputed, else i) | sign << 31;
-// n = scalars in this call, stride = points per window of the table.
+// n = scalars in this call, first = index of the first table point they apply to (a table may
+// hold several key queries back to back), stride = points per window of the table.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
-k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip, uint32_t n, uint32_t stride,
-         MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
+k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip, uint32_t n, uint32_t first,
+         uint32_t stride, MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (skip && skip[i]) return;
+  if (skip && skip[first + i]) return;
   uint32_t k[8];
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * (size_t)i);
   uint4 a = __ldg(sp), b = __ldg(sp + 1);
@@ -91,7 +92,7 @@ k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip,
     uint32_t bucket = (cfg.nwb == 1 ? 0u : (uint32_t)w * cfg.B) + d - 1;
     if (SCATTER) {
       uint32_t pos = atomicAdd(&counts_or_cursor[bucket], 1u);
-      uint32_t idx = (cfg.nwb == 1) ? (uint32_t)w * stride + i : i;
+      uint32_t idx = (cfg.nwb == 1) ? (uint32_t)w * stride + first + i : first + i;
       entries[pos] = idx | (neg << 31);
     } else {
       atomicAdd(&counts_or_cursor[bucket], 1u);
@@ -272,43 +273,41 @@ k_fix_partials(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucke
   store_vec(&bucket_sums[b], acc);
 }
 
-// Step 4c: heavy buckets, one warp each (grid-stride over the queue): lanes stride over the pieces,
-// a shared-memory tree adds the 32 lane sums: pieces / 32 + 5 sequential additions.
+// Step 4c: heavy buckets, one BLOCK each (grid-stride over the queue): threads stride over the
+// pieces, a shared-memory tree adds the per-thread sums: pieces / blockDim + log2(blockDim)
+// sequential additions (a 2^20-point MSM whose scalars are half ones has a 17 000-piece bucket).
 template <class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_fix_heavy(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums,
             const XYZZ<F>* __restrict__ partial, uint32_t nbuckets, uint32_t T,
             const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
   extern __shared__ uint4 smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
   const uint32_t count = *heavy_count;
   const uint32_t E = offsets[nbuckets];
   const uint32_t per = (E + T - 1) / T;
-  XYZZ<F>* w = sm + wib * 32;
-  for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + wib; q < count; q += nwarps) {   // warp-uniform
+  for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {   // block-uniform
     const uint32_t b = heavy_list[q];
     const uint32_t lo = offsets[b], hi = offsets[b + 1];
     const uint32_t t_first = lo / per, t_last = (hi - 1) / per;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t t = t_first + lane; t <= t_last; t += 32) {
+    for (uint32_t t = t_first + threadIdx.x; t <= t_last; t += blockDim.x) {
       const uint32_t slot = ((uint64_t)t * per >= lo) ? 0 : 1;
       XYZZ<F> p = load_vec_rw(&partial[2 * (size_t)t + slot]);
       acc.add(p);
     }
-    w[lane] = acc;
-    __syncwarp();
-    for (uint32_t stride = 16; stride > 0; stride >>= 1) {
-      if (lane < stride) {
-        XYZZ<F> a = w[lane];
-        a.add(w[lane + stride]);
-        w[lane] = a;
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
+      if (threadIdx.x < stride) {
+        XYZZ<F> a = sm[threadIdx.x];
+        a.add(sm[threadIdx.x + stride]);
+        sm[threadIdx.x] = a;
       }
-      __syncwarp();
+      __syncthreads();
     }
-    if (lane == 0) store_vec(&bucket_sums[b], w[0]);
-    __syncwarp();
+    if (threadIdx.x == 0) store_vec(&bucket_sums[b], sm[0]);
+    __syncthreads();
   }
 }
 
@@ -513,6 +512,12 @@ struct BaseTable {
   int acc_variant = 0;       // 0: 3 blocks/SM + prefetch, 1: 4 no prefetch, 2: 4 + prefetch, 3: 5 no prefetch
   int queued = 0;
   TailOutputs<F> outs{};
+  // batched-affine accumulation (msm_ba.cuh), selected by ZKB200_BATCHED_AFFINE
+  bool use_ba = false;
+  int ba_rounds = 0;
+  DevBuf<Affine<F>> ba_buf[2];
+  DevBuf<F> ba_scratch;
+  DevBuf<uint32_t> ba_off[2], ba_counts, ba_dummy;
   bool pipelined = false;    // false: every run() flushes immediately (plain stream order)
 
   static MsmConfig choose_config(uint32_t n, bool precompute, int force_c);
@@ -520,9 +525,10 @@ struct BaseTable {
             cudaStream_t st);
   void load_device_affine(const Affine<F>* d_affine, uint32_t n, bool precompute, int force_c, cudaStream_t st);
   void build_tables(cudaStream_t st);
-  // d_scalars: count * 32 B canonical little-endian; uses bases [0, count).
+  // d_scalars: count * 32 B canonical little-endian; uses bases [first, first + count).
   // d_result (nullable) receives the XYZZ sum, d_out_bytes (nullable) the RAW + COMP bytes.
-  void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes, cudaStream_t st);
+  void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes, cudaStream_t st,
+           uint32_t first = 0);
   // finish every queued MSM on `st` (batched tail); results are valid in stream order afterwards
   void join(cudaStream_t st);
   // stage timing (bench.py's roofline leg): when `profile` is set, run() brackets its stages with

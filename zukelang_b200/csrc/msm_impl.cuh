@@ -1,7 +1,12 @@
 // Host orchestration of the MSM pipeline (template bodies; included by msm_g1.cu / msm_g2.cu).
 #pragma once
+#include <algorithm>
 #include "msm.cuh"
+#include "msm_ba.cuh"
 
+#ifndef ZK_BATCHED_AFFINE_DEFAULT
+#define ZK_BATCHED_AFFINE_DEFAULT 0
+#endif
 #ifndef ZK_ACC_VARIANT_DEFAULT
 #define ZK_ACC_VARIANT_DEFAULT 1
 #endif
@@ -136,12 +141,34 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   window_sums.alloc((size_t)MSM_QUEUE * (cfg.nwb + 1));
   queued = 0;
   pipelined = env_int("ZKB200_PIPELINE", 0) != 0;
+  use_ba = env_int("ZKB200_BATCHED_AFFINE", ZK_BATCHED_AFFINE_DEFAULT) != 0;
+  if (use_ba) {
+    uint64_t E = (uint64_t)n * cfg.W;
+    uint64_t avg = E / nb + 1;
+    int R = 1;
+    while ((1ull << R) < 2 * avg) R++;
+    R += 1;
+    int env_r = env_int("ZKB200_BA_ROUNDS", -1);
+    if (env_r >= 0) R = env_r;
+    if (R > 24) R = 24;
+    ba_rounds = R;
+    // per-round output bound b_{r+1} = b_r / 2 + nb + 1 starts at E / 2 + nb + 1 and tends to 2 nb + 2
+    uint64_t out0 = std::max<uint64_t>(E / 2 + nb + 2, 2ull * nb + 4);
+    uint64_t out1 = std::max<uint64_t>(out0 / 2 + nb + 2, 2ull * nb + 4);
+    ba_buf[0].alloc(out0);
+    ba_buf[1].alloc(out1);
+    ba_scratch.alloc((size_t)BA_K * (cdiv(out0, BA_K) + 1));
+    ba_off[0].alloc(nb + 1);
+    ba_off[1].alloc(nb + 1);
+    ba_counts.alloc(nb);
+    ba_dummy.alloc(nb);
+  }
 }
 
 template <class T>
 void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes,
-                       cudaStream_t st) {
-  ZK_REQUIRE(count > 0 && count <= n, ZK_EARG, "scalar count exceeds the base table");
+                       cudaStream_t st, uint32_t first) {
+  ZK_REQUIRE(count > 0 && (uint64_t)first + count <= n, ZK_EARG, "scalar range exceeds the base table");
   const uint32_t nb = cfg.nbuckets();
   if (queued == MSM_QUEUE) join(st);
   const int slot = queued;
@@ -151,15 +178,44 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   // ---- sort and accumulate -----------------------------------------------------------------
   mark(0);
   ZK_CUDA(cudaMemsetAsync(counts.p, 0, nb * sizeof(uint32_t), st));
-  k_digits<false><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, counts.p, nullptr);
+  k_digits<false><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, first, n, cfg, counts.p, nullptr);
   uint32_t ntiles = cdiv(nb, SCAN_TILE);
   k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p);
   k_scan_spine<<<1, 1024, 0, st>>>(tile_sums.p, ntiles);
   k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p, offsets.p, cursor.p);
-  k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, n, cfg, cursor.p, entries.p);
+  k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, first, n, cfg, cursor.p, entries.p);
   mark(1);
   XYZZ<F>* bsum = bucket_sums.p + (size_t)slot * nb;
-  const uint32_t grid = acc_blocks;
+  if (use_ba) {
+    // rounds of pairwise affine additions inside the buckets, shared inversions (msm_ba.cuh)
+    const uint32_t* in_off = offsets.p;
+    uint64_t bound = (uint64_t)count * cfg.W;       // entries of round 0
+    for (int r = 0; r < ba_rounds; r++) {
+      uint32_t* out_off = ba_off[r & 1].p;
+      k_ba_next_counts<<<cdiv(nb, 256), 256, 0, st>>>(in_off, nb, ba_counts.p);
+      k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(ba_counts.p, nb, tile_sums.p);
+      k_scan_spine<<<1, 1024, 0, st>>>(tile_sums.p, ntiles);
+      k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(ba_counts.p, nb, tile_sums.p, out_off, ba_dummy.p);
+      bound = bound / 2 + nb + 1;
+      uint32_t nthr = cdiv(bound, BA_K);
+      if (r == 0)
+        k_ba_round<F, true><<<cdiv(nthr, 128), 128, 0, st>>>(pts.p, entries.p, nullptr, in_off, out_off, nb, ba_buf[0].p,
+                                                             ba_scratch.p, nthr);
+      else
+        k_ba_round<F, false><<<cdiv(nthr, 128), 128, 0, st>>>(nullptr, nullptr, ba_buf[(r - 1) & 1].p, in_off, out_off, nb,
+                                                              ba_buf[r & 1].p, ba_scratch.p, nthr);
+      in_off = out_off;
+    }
+    if (ba_rounds == 0)
+      k_ba_finish<F, true><<<cdiv(nb, 128), 128, 0, st>>>(pts.p, entries.p, nullptr, in_off, nb, bsum);
+    else
+      k_ba_finish<F, false><<<cdiv(nb, 128), 128, 0, st>>>(nullptr, nullptr, ba_buf[(ba_rounds - 1) & 1].p, in_off, nb, bsum);
+  } else {
+  // one wave at most; for small inputs fewer blocks, so that a slice still holds >= 16 entries
+  // (otherwise the partial fix-up, not the mixed adds, would end up doing the additions)
+  uint32_t grid = cdiv((uint64_t)count * cfg.W, 16 * 128);
+  if (grid > acc_blocks) grid = acc_blocks;
+  if (grid < 1) grid = 1;
   switch (acc_variant) {
     case 4: k_accumulate<F, 2, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
     case 5: k_accumulate<F, 1, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
@@ -170,8 +226,12 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   }
   ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));
   k_fix_partials<F><<<cdiv(nb, 128), 128, 0, st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p, heavy.p + 1);
-  k_fix_heavy<F><<<sm_count(), 128, 128 * sizeof(XYZZ<F>), st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p,
-                                                                   heavy.p + 1);
+  {
+    const int ht = sizeof(XYZZ<F>) > 192 ? 128 : 256;   // 48 KB of shared memory either way
+    k_fix_heavy<F><<<sm_count(), ht, ht * sizeof(XYZZ<F>), st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p,
+                                                                 heavy.p + 1);
+  }
+  }
   mark(2);
   // ---- queue the tail ------------------------------------------------------------------------
   outs.result[slot] = d_result ? d_result : window_sums.p + (size_t)slot * (cfg.nwb + 1) + cfg.nwb;
@@ -240,7 +300,7 @@ BaseTable<T>::~BaseTable() {
 template <class T>
 size_t BaseTable<T>::device_bytes() const {
   return pts.bytes() + skip.bytes() + counts.bytes() + offsets.bytes() + cursor.bytes() + tile_sums.bytes() +
-         entries.bytes() + heavy.bytes() + bucket_sums.bytes() + partial.bytes() + chunk_out.bytes() + tree_tmp.bytes() + window_sums.bytes();
+         entries.bytes() + heavy.bytes() + bucket_sums.bytes() + partial.bytes() + chunk_out.bytes() + tree_tmp.bytes() + window_sums.bytes() + ba_buf[0].bytes() + ba_buf[1].bytes() + ba_scratch.bytes();
 }
 
 template <class T>

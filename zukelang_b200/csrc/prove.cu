@@ -268,12 +268,13 @@ struct PinLayout {
 struct PinocchioKey : HandleBase {
   PinLayout lay;
   uint32_t m = 0, n_mid = 0;
-  // G1 queries: vv, yy, vavv, yayy, bvwy, h ; G2 queries: ww, waww
-  Query<G1Traits> q_vv, q_yy, q_vav, q_yay, q_bvwy, q_h;
-  Query<G2Traits> q_ww, q_waw;
+  // All G1 queries live back to back in ONE table (likewise the two G2 queries), each proof element
+  // is an MSM over its range: the six (two) latency-bound tails then run as one batched launch.
+  // G1 ranges: 0 vv, 1 yy, 2 vav, 3 yay, 4 bvwy, 5 h ; G2 ranges: 0 ww, 1 waw
+  Query<G1Traits> q1;
+  Query<G2Traits> q2;
+  uint32_t first1[6], cnt1[6], first2[2], cnt2[2];
   DevBuf<uint32_t> mid_index, d_sol, d_d;
-  DevBuf<XYZZ<Fp>> r1;   // vv, yy, h, vavv, yayy, bvwy
-  DevBuf<XYZZ<Fp2>> r2;  // ww, waww
   DevBuf<uint8_t> d_out;
   PinocchioKey() { kind = 5; }
 };
@@ -342,39 +343,42 @@ int zk_pinocchio_pk_load(const zk_pinocchio_pkey* pk, int shard_index, int shard
   slice(pk->n + 1, shard_index, shard_count, &L.si_lo, &L.si_cnt);
   slice(pk->m, shard_index, shard_count, &L.all_lo, &L.all_cnt);
   L.singles = shard_index == 0;
-  auto g1q = [&](Query<G1Traits>& q, std::initializer_list<const uint8_t*> singles, const uint8_t* list) {
-    std::vector<uint8_t> raw;
-    for (const uint8_t* sp : singles) append(raw, sp, 96);
-    if (L.mid_cnt) append(raw, list + (size_t)L.mid_lo * 96, (size_t)L.mid_cnt * 96);
-    q.load(raw, (uint32_t)singles.size() + L.mid_cnt, st);
+  std::vector<uint8_t> raw1, raw2;
+  uint32_t at1 = 0, at2 = 0;
+  auto g1q = [&](int slot, std::initializer_list<const uint8_t*> singles, const uint8_t* list) {
+    for (const uint8_t* sp : singles) append(raw1, sp, 96);
+    if (L.mid_cnt) append(raw1, list + (size_t)L.mid_lo * 96, (size_t)L.mid_cnt * 96);
+    k->first1[slot] = at1;
+    k->cnt1[slot] = (uint32_t)singles.size() + L.mid_cnt;
+    at1 += k->cnt1[slot];
   };
-  auto g2q = [&](Query<G2Traits>& q, const uint8_t* single, const uint8_t* list) {
-    std::vector<uint8_t> raw;
-    append(raw, single, 192);
-    if (L.mid_cnt) append(raw, list + (size_t)L.mid_lo * 192, (size_t)L.mid_cnt * 192);
-    q.load(raw, 1 + L.mid_cnt, st);
+  auto g2q = [&](int slot, const uint8_t* single, const uint8_t* list) {
+    append(raw2, single, 192);
+    if (L.mid_cnt) append(raw2, list + (size_t)L.mid_lo * 192, (size_t)L.mid_cnt * 192);
+    k->first2[slot] = at2;
+    k->cnt2[slot] = 1 + L.mid_cnt;
+    at2 += k->cnt2[slot];
   };
-  g1q(k->q_vv, {pk->vt}, pk->vv);
-  g1q(k->q_yy, {pk->yt}, pk->yy);
-  g1q(k->q_vav, {pk->vavt}, pk->vav);
-  g1q(k->q_yay, {pk->yayt}, pk->yay);
-  g1q(k->q_bvwy, {pk->vbt, pk->wbt, pk->ybt}, pk->bvwy);
-  g2q(k->q_ww, pk->wt, pk->ww);
-  g2q(k->q_waw, pk->wawt, pk->waw);
-  {
-    std::vector<uint8_t> raw;
-    append(raw, pk->one, 96);
-    append(raw, pk->si + (size_t)L.si_lo * 96, (size_t)L.si_cnt * 96);
-    append(raw, pk->v_all + (size_t)L.all_lo * 96, (size_t)L.all_cnt * 96);
-    append(raw, pk->w_all + (size_t)L.all_lo * 96, (size_t)L.all_cnt * 96);
-    k->q_h.load(raw, 1 + L.si_cnt + 2 * L.all_cnt, st);
-  }
+  g1q(0, {pk->vt}, pk->vv);
+  g1q(1, {pk->yt}, pk->yy);
+  g1q(2, {pk->vavt}, pk->vav);
+  g1q(3, {pk->yayt}, pk->yay);
+  g1q(4, {pk->vbt, pk->wbt, pk->ybt}, pk->bvwy);
+  append(raw1, pk->one, 96);
+  append(raw1, pk->si + (size_t)L.si_lo * 96, (size_t)L.si_cnt * 96);
+  append(raw1, pk->v_all + (size_t)L.all_lo * 96, (size_t)L.all_cnt * 96);
+  append(raw1, pk->w_all + (size_t)L.all_lo * 96, (size_t)L.all_cnt * 96);
+  k->first1[5] = at1;
+  k->cnt1[5] = 1 + L.si_cnt + 2 * L.all_cnt;
+  at1 += k->cnt1[5];
+  g2q(0, pk->wt, pk->ww);
+  g2q(1, pk->wawt, pk->waw);
+  k->q1.load(raw1, at1, st);
+  k->q2.load(raw2, at2, st);
   k->mid_index.alloc(pk->n_mid ? pk->n_mid : 1);
   if (pk->n_mid) ZK_CUDA(cudaMemcpyAsync(k->mid_index.p, pk->mid_index, pk->n_mid * 4, cudaMemcpyHostToDevice, st));
   k->d_sol.alloc((size_t)pk->m * 8);
   k->d_d.alloc(24);
-  k->r1.alloc(6);
-  k->r2.alloc(2);
   k->d_out.alloc(ZK_PINOCCHIO_PROOF_OUT);
   ZK_CUDA(cudaStreamSynchronize(st));
   *handle = register_handle(std::move(k));
@@ -400,17 +404,29 @@ int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* s
   ZK_CUDA(cudaMemcpyAsync(k->d_d.p, dd, 96, cudaMemcpyHostToDevice, st));
   q.eval(k->d_sol.p, st);
   uint32_t span = std::max(std::max(L.mid_cnt, L.si_cnt), std::max(L.all_cnt, 1u));
+  uint32_t* s1 = k->q1.scalars.p;
+  uint32_t* s2 = k->q2.scalars.p;
+  auto at1 = [&](int slot) { return s1 + 8 * (size_t)k->first1[slot]; };
+  auto at2 = [&](int slot) { return s2 + 8 * (size_t)k->first2[slot]; };
   k_pinocchio_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, q.H.p, q.target.p, k->d_sol.p, k->mid_index.p, k->d_d.p,
-                                                        k->q_vv.scalars.p, k->q_ww.scalars.p, k->q_yy.scalars.p,
-                                                        k->q_vav.scalars.p, k->q_waw.scalars.p, k->q_yay.scalars.p,
-                                                        k->q_bvwy.scalars.p, k->q_h.scalars.p);
-  // output order: vv ww yy h vavv waww yayy bvwy; every query's tail overlaps the next accumulation
+                                                        at1(0), at2(0), at1(1), at1(2), at2(1), at1(3), at1(4), at1(5));
+  // output order: vv ww yy h vavv waww yayy bvwy (pinocchio.ml:195-208)
   uint8_t* o = k->d_out.p;
-  auto run1 = [&](Query<G1Traits>& qq) { qq.table.pipelined = true; qq.table.run(qq.scalars.p, qq.table.n, nullptr, o, st); o += ZK_G1_OUT; };
-  auto run2 = [&](Query<G2Traits>& qq) { qq.table.pipelined = true; qq.table.run(qq.scalars.p, qq.table.n, nullptr, o, st); o += ZK_G2_OUT; };
-  run1(k->q_vv); run2(k->q_ww); run1(k->q_yy); run1(k->q_h); run1(k->q_vav); run2(k->q_waw); run1(k->q_yay); run1(k->q_bvwy);
-  k->q_vv.table.join(st); k->q_ww.table.join(st); k->q_yy.table.join(st); k->q_h.table.join(st);
-  k->q_vav.table.join(st); k->q_waw.table.join(st); k->q_yay.table.join(st); k->q_bvwy.table.join(st);
+  uint8_t* o_vv = o;                       o += ZK_G1_OUT;
+  uint8_t* o_ww = o;                       o += ZK_G2_OUT;
+  uint8_t* o_yy = o;                       o += ZK_G1_OUT;
+  uint8_t* o_h = o;                        o += ZK_G1_OUT;
+  uint8_t* o_vav = o;                      o += ZK_G1_OUT;
+  uint8_t* o_waw = o;                      o += ZK_G2_OUT;
+  uint8_t* o_yay = o;                      o += ZK_G1_OUT;
+  uint8_t* o_bvwy = o;
+  k->q1.table.pipelined = k->q2.table.pipelined = true;
+  auto run1 = [&](int slot, uint8_t* out) { k->q1.table.run(at1(slot), k->cnt1[slot], nullptr, out, st, k->first1[slot]); };
+  auto run2 = [&](int slot, uint8_t* out) { k->q2.table.run(at2(slot), k->cnt2[slot], nullptr, out, st, k->first2[slot]); };
+  run1(0, o_vv); run1(1, o_yy); run1(5, o_h); run1(2, o_vav); run1(3, o_yay); run1(4, o_bvwy);
+  run2(0, o_ww); run2(1, o_waw);
+  k->q1.table.join(st);   // one batched tail for the six G1 elements
+  k->q2.table.join(st);   // one for the two G2 elements
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_PINOCCHIO_PROOF_OUT, cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));
