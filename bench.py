@@ -250,7 +250,7 @@ def run_gpu_arm(args):
         tot = sum(a * d for a, d in zip(ints, dl_all)) % R
         host = torch.from_numpy(np.ascontiguousarray(w[lo:hi]).view(np.int64)).pin_memory()
         batches.append({"host": host, "dev": host.cuda(), "expect_dlog": tot})
-    QUEUE = 8                                           # zk_table_pipeline batches up to 8 tails
+    QUEUE = 16                                          # zk_table_pipeline batches up to 16 tails
     d_ring = torch.zeros(QUEUE, 144, dtype=torch.uint8, device="cuda")    # one result slot per queued MSM
     p_ring = torch.zeros(QUEUE, 96, dtype=torch.uint8, device="cuda")     # partial sums to gather (N > 1)
     g_ring = torch.zeros(world, QUEUE, 96, dtype=torch.uint8, device="cuda")
@@ -260,7 +260,7 @@ def run_gpu_arm(args):
 
     def run_steps(batch_ids):
         """One MSM per entry of batch_ids, device-resident scalars, on stream `side`.
-        Pipelined: groups of up to 8 MSMs sort + accumulate back to back, then ONE batched tail
+        Pipelined: groups of up to 16 MSMs sort + accumulate back to back, then ONE batched tail
         (zk_table_join) finishes the group; for N > 1 the group's partial sums travel in one
         all_gather and are added by one batched kernel.  Returns the last result tensor."""
         group = QUEUE if pipelined else 1

@@ -89,8 +89,8 @@ int zk_table_info(uint64_t handle, uint64_t info[8]);
 /* Pipelining of consecutive *_msm_dev calls on one table.  Each MSM ends in a latency-bound
  * tail (bucket reduction, window combine, affine conversion: ~40 dependent point operations) whose
  * wall time is the same for one MSM as for a batch.  With enable = 0 (default) every call runs its
- * own tail: plain stream order.  With enable != 0 a call only sorts and accumulates into one of 8
- * bucket buffers and queues its tail; zk_table_join(handle, cuda_stream) (or the 9th call) runs
+ * own tail: plain stream order.  With enable != 0 a call only sorts and accumulates into one of 16
+ * bucket buffers and queues its tail; zk_table_join(handle, cuda_stream) (or the 17th call) runs
  * ONE batched tail for everything queued.  d_out of a queued call is valid on cuda_stream after
  * the join. */
 int zk_table_pipeline(uint64_t handle, int enable);

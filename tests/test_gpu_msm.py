@@ -152,3 +152,60 @@ def test_table_msm_batch_and_pipelined_dev(zk):
         _lib.check(zk.zk_table_pipeline(h.value, 0))
     finally:
         _lib.check(zk.zk_table_free(h.value))
+
+
+def test_g1_msm_full_size_2e20_known_dlog(zk):
+    """BASELINE's headline size: 2^20 points, uniform scalars, resident precomputed table.  No CPU
+    oracle can fold 2^20 scalar multiplications in seconds, so the check is the size-independent
+    identity  sum s_i (d_i G) = (sum s_i d_i mod r) G  plus linearity  MSM(s) + MSM(t) = MSM(s + t)."""
+    import numpy as np
+    from zukelang_b200 import _lib
+    n = 1 << 20
+    rng = np.random.Generator(np.random.PCG64(20))
+
+    def scalars():
+        w = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        w[:, 3] &= np.uint64((1 << 61) - 1)                  # < 2^253 < r : canonical, sums stay canonical
+        ints = [int(a) | (int(b) << 64) | (int(c) << 128) | (int(d) << 192) for a, b, c, d in w.tolist()]
+        return w, ints
+
+    dl_w, dl = scalars()
+    bases = np.empty(n * 96, dtype=np.uint8)
+    _lib.check(zk.zk_g1_fixed_base_mul(dl_w.ctypes.data, n, bases.ctypes.data))
+    h = ctypes.c_uint64()
+    _lib.check(zk.zk_g1_table_load(bases.ctypes.data, None, n, 1, 0, ctypes.byref(h)))
+    try:
+        s_w, s = scalars()
+        t_w, t = scalars()
+        u = [(a + b) % R for a, b in zip(s, t)]
+        u_w = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in u), dtype=np.uint64).copy()
+        outs = []
+        for w in (s_w, t_w, u_w):
+            out = H.out_buf(144)
+            _lib.check(zk.zk_g1_table_msm(h.value, w.ctypes.data, n, out))
+            outs.append(bytes(out))
+        exp = np.empty(96 * 3, dtype=np.uint8)
+        tots = [sum(a * b for a, b in zip(v, dl)) % R for v in (s, t, u)]
+        _lib.check(zk.zk_g1_fixed_base_mul(H.scalars_bytes(tots), 3, exp.ctypes.data))
+        for i in range(3):
+            assert outs[i][:96] == bytes(exp[96 * i:96 * (i + 1)])
+        both = H.out_buf(144)                                # linearity through the point adder
+        _lib.check(zk.zk_g1_sum(outs[0][:96] + outs[1][:96], 2, both))
+        assert bytes(both) == outs[2]
+    finally:
+        _lib.check(zk.zk_table_free(h.value))
+
+
+def test_point_sums(zk):
+    from zukelang_b200 import _lib
+    rng = random.Random(12)
+    for gname, G, enc, expect, fn, outn in (("G1", O.G1, H.g1_bytes, H.expect_g1, "zk_g1_sum", 144),
+                                            ("G2", O.G2, H.g2_bytes, H.expect_g2, "zk_g2_sum", 288)):
+        pts = [G.mul(G.one, rng.randrange(R)) for _ in range(5)] + [None]
+        pts.append(G.neg(pts[0]))
+        pts.append(pts[1])                                   # repeated point: doubling branch
+        out = H.out_buf(outn)
+        _lib.check(getattr(zk, fn)(enc(pts), len(pts), out))
+        assert bytes(out) == expect(G.sum(pts))
+    bad = bytes(95) + b"\x01"
+    assert zk.zk_g1_sum(bad, 1, H.out_buf(144)) == _lib.ZK_EPOINT

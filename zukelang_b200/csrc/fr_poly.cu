@@ -146,21 +146,29 @@ void NttPlan::inverse(Fr* d, cudaStream_t st) const { ntt_inverse_batch(*this, d
 // QAP.ml:121-131 eval':  out[i] = sum_k sol[k] * M[k][i]; blockIdx.y selects V / W / Y.
 // Writes the n coefficients to coeffs (kept for the MSM scalars) and a zero-padded,
 // coset-shifted copy of length D to work (input of the forward NTT).
-static __global__ void __launch_bounds__(128)
+constexpr int COMBINE_X = 32, COMBINE_K = 8;   // block = 32 coefficients x 8 slices of the variable range
+static __global__ void __launch_bounds__(COMBINE_X * COMBINE_K)
 k_qap_combine(const Fr* __restrict__ vm, const Fr* __restrict__ wm, const Fr* __restrict__ ym,
               const Fr* __restrict__ sol, uint32_t m, uint32_t n, uint32_t D, const Fr* __restrict__ coset,
               Fr* __restrict__ coeffs, Fr* __restrict__ work) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= D) return;
-  int which = blockIdx.y;
+  __shared__ Fr part[COMBINE_K][COMBINE_X];
+  const uint32_t i = blockIdx.x * COMBINE_X + threadIdx.x;
+  const int which = blockIdx.y;
   Fr acc = Fr::zero();
   if (i < n) {
     const Fr* M = which == 0 ? vm : (which == 1 ? wm : ym);
-    for (uint32_t k = 0; k < m; k++) {
+    for (uint32_t k = threadIdx.y; k < m; k += COMBINE_K) {   // adjacent threadIdx.x read adjacent coefficients
       Fr s = load_vec(&sol[k]);
       if (s.is_zero()) continue;
       acc = acc + s * load_vec(&M[(size_t)k * n + i]);
     }
+  }
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y != 0 || i >= D) return;
+#pragma unroll
+  for (int q = 1; q < COMBINE_K; q++) acc = acc + part[q][threadIdx.x];
+  if (i < n) {
     store_vec(&coeffs[(size_t)which * n + i], acc);
     acc = acc * load_vec(&coset[i]);
   }
@@ -468,7 +476,8 @@ void QapDevice::eval(const uint32_t* d_sol_raw, cudaStream_t st) {
   const uint32_t D = plan.D;
   ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
   fr_to_mont(d_sol_raw, sol_m.p, m, flag.p, st);
-  k_qap_combine<<<dim3(cdiv(D, 128), 3), 128, 0, st>>>(vm.p, wm.p, ym.p, sol_m.p, m, n, D, plan.coset.p, Vc.p, V.p);
+  k_qap_combine<<<dim3(cdiv(D, COMBINE_X), 3), dim3(COMBINE_X, COMBINE_K), 0, st>>>(vm.p, wm.p, ym.p, sol_m.p, m, n, D,
+                                                                                     plan.coset.p, Vc.p, V.p);
   quotient_from_work(st);
 }
 

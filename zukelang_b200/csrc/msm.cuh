@@ -378,7 +378,7 @@ k_reduce_tree(const XYZZ<F>* __restrict__ in, uint32_t n_in, size_t in_stride, X
 }
 
 // Output slots of the queued MSMs (passed by value to the batched tail kernels).
-constexpr int MSM_QUEUE = 8;
+constexpr int MSM_QUEUE = 16;
 template <class F>
 struct TailOutputs {
   XYZZ<F>* result[MSM_QUEUE];   // XYZZ sum (always set: caller's slot or table scratch)
