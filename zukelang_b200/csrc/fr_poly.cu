@@ -20,25 +20,12 @@ static __global__ void k_fr_from_mont(const Fr* __restrict__ in, uint32_t* __res
   Fr a = load_vec_rw(&in[i]);
   store_vec(reinterpret_cast<Fr*>(raw) + i, a.from_mont());
 }
-static __global__ void k_fr_axpby(const Fr* a, const Fr* __restrict__ x, const Fr* b, const Fr* __restrict__ y,
-                                  Fr* __restrict__ out, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fr r = load_vec_rw(a) * load_vec_rw(&x[i]);
-  if (y) r = r + load_vec_rw(b) * load_vec_rw(&y[i]);
-  store_vec(&out[i], r);
-}
-
 void fr_to_mont(const uint32_t* d_raw, Fr* d_out, uint32_t n, int* d_err, cudaStream_t st) {
   if (n) k_fr_to_mont<<<cdiv(n, 256), 256, 0, st>>>(d_raw, d_out, n, d_err);
 }
 void fr_from_mont(const Fr* d_in, uint32_t* d_raw, uint32_t n, cudaStream_t st) {
   if (n) k_fr_from_mont<<<cdiv(n, 256), 256, 0, st>>>(d_in, d_raw, n);
 }
-void fr_axpby(const Fr* a, const Fr* x, const Fr* b, const Fr* y, Fr* out, uint32_t n, cudaStream_t st) {
-  if (n) k_fr_axpby<<<cdiv(n, 256), 256, 0, st>>>(a, x, b, y, out, n);
-}
-
 __device__ __noinline__ Fr fr_pow_u32(const Fr& base, uint32_t e) {
   Fr acc = Fr::one();
   if (e == 0) return acc;

@@ -96,7 +96,5 @@ struct QapHandle : HandleBase {
 // canonical little-endian bytes <-> Montgomery vectors (device buffers)
 void fr_to_mont(const uint32_t* d_raw, Fr* d_out, uint32_t n, int* d_err, cudaStream_t st);
 void fr_from_mont(const Fr* d_in, uint32_t* d_raw, uint32_t n, cudaStream_t st);
-// out[i] = a * x[i] + b * y[i]   (a, b device scalars in Montgomery form; y may be null)
-void fr_axpby(const Fr* a, const Fr* x, const Fr* b, const Fr* y, Fr* out, uint32_t n, cudaStream_t st);
 
 }  // namespace zk

@@ -30,7 +30,7 @@ struct MsmConfig {
   int W;        // number of windows  = ceil(256 / c)
   int nwb;      // bucket windows: 1 when precomputed, else W
   uint32_t B;   // buckets per window = 2^(c-1)
-  int S;        // (unused since the balanced accumulation; kept for the info record)
+  int S;        // always 1 (the balanced accumulation has no per-bucket segments); kept in zk_table_info
   int L;        // buckets per thread in the chunk reduction
   __host__ __device__ uint32_t nbuckets() const { return (uint32_t)nwb * B; }
 };
@@ -434,14 +434,6 @@ k_parse_bases(const uint8_t* __restrict__ raw, const uint8_t* __restrict__ inf_f
   skip[i] = p.is_inf() ? 1 : 0;
 }
 
-template <class F>
-__global__ void k_mark_skip(const Affine<F>* __restrict__ pts, uint32_t n, uint8_t* __restrict__ skip) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Affine<F> p = load_vec_rw(&pts[i]);
-  skip[i] = p.is_inf() ? 1 : 0;
-}
-
 // window w of the precomputed table from window w-1:  P -> 2^c * P   (XYZZ scratch)
 template <class F>
 __global__ void __launch_bounds__(128)
@@ -523,7 +515,6 @@ struct BaseTable {
   static MsmConfig choose_config(uint32_t n, bool precompute, int force_c);
   void load(const uint8_t* host_raw, const uint8_t* host_inf, uint32_t n, bool precompute, int force_c,
             cudaStream_t st);
-  void load_device_affine(const Affine<F>* d_affine, uint32_t n, bool precompute, int force_c, cudaStream_t st);
   void build_tables(cudaStream_t st);
   // d_scalars: count * 32 B canonical little-endian; uses bases [first, first + count).
   // d_result (nullable) receives the XYZZ sum, d_out_bytes (nullable) the RAW + COMP bytes.

@@ -85,23 +85,6 @@ void BaseTable<T>::load(const uint8_t* host_raw, const uint8_t* host_inf, uint32
 }
 
 template <class T>
-void BaseTable<T>::load_device_affine(const Affine<F>* d_affine, uint32_t n_, bool precompute, int force_c,
-                                      cudaStream_t st) {
-  ZK_REQUIRE(n_ > 0, ZK_EARG, "empty base table");
-  n = n_;
-  precomputed = precompute;
-  cfg = choose_config(n, precompute, force_c);
-  size_t nwin = precompute ? cfg.W : 1;
-  ZK_REQUIRE((uint64_t)nwin * n < (1ull << 31), ZK_EARG, "table too large for 31-bit point indices");
-  pts.alloc(nwin * n);
-  skip.alloc(n);
-  ZK_CUDA(cudaMemcpyAsync(pts.p, d_affine, (size_t)n * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, st));
-  k_mark_skip<F><<<cdiv(n, 256), 256, 0, st>>>(pts.p, n, skip.p);
-  ZK_CUDA(cudaGetLastError());
-  build_tables(st);
-}
-
-template <class T>
 void BaseTable<T>::build_tables(cudaStream_t st) {
   if (precomputed) {
     DevBuf<XYZZ<F>> scratch(n);
