@@ -94,7 +94,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -102,13 +102,17 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_start=None, t_end=None):
+        """Summary of the samples that arrived inside [t_start, t_end] (the timed region); falls back
+        to the busiest half of all samples when the region was shorter than the sampling period."""
         if self.proc:
             self.proc.terminate()
+        inside = [r for ts, r in self.rows if t_start is not None and t_start - 0.05 <= ts <= t_end + 0.15]
+        rows = inside if inside else [r for _, r in self.rows]
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx = max(mx, float(r[2]))
@@ -119,10 +123,9 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        # "under load": keep the upper half of the samples (idle samples before/after sit at the bottom)
-        load = sm[len(sm) // 2:] if sm else []
+        load = sm if inside else (sm[len(sm) // 2:] if sm else [])
         return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -225,6 +228,8 @@ def run_gpu_arm(args):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     zk = _lib.lib()
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                     # nvidia-smi takes a second to come up: start it first
     n_total = 1 << args.logn
     lo, hi = n_total * rank // world, n_total * (rank + 1) // world
     n = hi - lo
@@ -300,8 +305,6 @@ def run_gpu_arm(args):
         peak_imad = max(peak_imad, ops.value)
     peak_mac32 = peak_imad / 2.0                       # one MAC32 = mad.lo + mad.hi
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     # ---- warm-up, with the exact known-dlog check -------------------------------------------
     _lib.check(zk.zk_table_pipeline(handle.value, 1 if pipelined else 0))
     with torch.cuda.stream(side):
@@ -316,13 +319,15 @@ def run_gpu_arm(args):
     slots = [(args.warmup + it) % pool for it in range(args.steps)]   # scalar batch of every step
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.time()
     with torch.cuda.stream(side):
         e0.record(side)
         res = run_steps(slots)
         e1.record(side)
     barrier()
+    t_region1 = time.time()
     dev_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, t_region1)
     assert combine(res) == expected_point(batches[slots[-1]]["expect_dlog"])
     # stage times of the dominant kernel: a few more steps, one at a time, with stage events on
     acc_ms, stages_last = [], None
@@ -379,6 +384,19 @@ def run_gpu_arm(args):
 
     if rank == 0:
         c, W = int(info[0]), int(info[1])
+        # kernels of libzkb200 launched in the timed region: 8 per MSM (2 digit passes, 3 scan kernels,
+        # accumulate, 2 partial fix-ups) + one batched tail per group (reduce chunks, tree levels,
+        # combine+finalize) + the shard sum for N > 1
+        group = QUEUE if pipelined else 1
+        groups = (args.steps + group - 1) // group
+        cpw = (1 << (c - 1)) // (16 if (pipelined and min(group, args.steps) >= 3) else 4)
+        levels, cnt = 0, cpw
+        while True:
+            levels += 1
+            cnt = (cnt + 63) // 64
+            if cnt == 1:
+                break
+        gpu_launches = 8 * args.steps + groups * (2 + levels + (1 if world > 1 else 0))
         acc_avg = sum(acc_ms) / len(acc_ms)
         achieved = n * MAC32_PER_POINT / (acc_avg * 1e-3) / 1e12
         peaks = {}
@@ -405,7 +423,7 @@ def run_gpu_arm(args):
                     "api": "zk_g1_table_msm_batch: K host scalar vectors (pinned) in, K points out, uploads double-buffered",
                     "h2d_gbs_measured": h2d_gbs, "h2d_bound_mpts": h2d_gbs * 1e9 / 32 / 1e6 * world,
                     "ms_per_step": e2e_s / args.steps * 1e3},
-            "gpu_launches": 14 * args.steps,
+            "gpu_launches": gpu_launches,
             "roofline": {"bound": "int32-imad", "kernel": "k_accumulate<Fp>", "achieved": achieved,
                          "peak": peak_mac32 / 1e12, "unit": "TMAC32/s", "frac": achieved / (peak_mac32 / 1e12),
                          "traffic": (NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.logn == 20 and c == 17) else None),

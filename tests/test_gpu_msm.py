@@ -121,7 +121,7 @@ def test_table_msm_batch_and_pipelined_dev(zk):
     import numpy as np
     import torch
     from zukelang_b200 import _lib
-    n, count = 3000, 11
+    n, count = 3000, 19
     rng = random.Random(77)
     dl = [rng.randrange(R) for _ in range(n)]
     bases = (ctypes.c_uint8 * (96 * n))()
