@@ -447,11 +447,11 @@ def run_gpu_arm(args):
                 line["groth16"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            sample = 1 << 14
+            sample = 1 << 15
             sc_raw = batches[0]["host"].numpy().tobytes()[:sample * 32]
             secs, out = cpu_fold_msm(bases[:sample * 96].tobytes(), sc_raw, sample, threads)
             line["cpu_baseline"] = {"value": sample / secs / 1e6, "unit": "Mpts/s", "cores": threads, "kind": "port",
-                                    "sample": "first 2^14 of the 2^20 points, oracle/c fold of double-and-add scalar muls "
+                                    "sample": "first 2^15 of the 2^20 points, oracle/c fold of double-and-add scalar muls "
                                               "(curve.ml:91-118) on all host threads, %.1f s" % secs}
         print(json.dumps(line), flush=True)
     _lib.check(zk.zk_table_free(handle.value))
