@@ -199,7 +199,7 @@ def run_reference_arm(args):
                              "sample": "2^12 of the 2^20 points per step, oracle/c fold-MSM on all host threads"},
             "e2e": {"value": val, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -453,14 +453,22 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": sample / secs / 1e6, "unit": "Mpts/s", "cores": threads, "kind": "port",
                                     "sample": "first 2^15 of the 2^20 points, oracle/c fold of double-and-add scalar muls "
                                               "(curve.ml:91-118) on all host threads, %.1f s" % secs}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     _lib.check(zk.zk_table_free(handle.value))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_OUT = sys.stdout
+
+
 def main():
+    global _JSON_OUT
+    # stdout carries exactly ONE line, the JSON record: keep a private handle on the real stdout and
+    # point fd 1 at stderr so that library chatter (e.g. NCCL's version banner) cannot precede it
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
