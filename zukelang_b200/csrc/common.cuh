@@ -39,6 +39,8 @@ struct Error {
 // library-wide stream (created by zk_init; every kernel of a call is ordered on it
 // unless the caller passes its own stream to a *_dev entry point)
 cudaStream_t default_stream();
+cudaStream_t fork_aux(cudaStream_t st);   // auxiliary stream, ordered after the work enqueued on st so far
+void join_aux(cudaStream_t st);           // st waits for the auxiliary stream
 int sm_count();
 
 // RAII device buffer

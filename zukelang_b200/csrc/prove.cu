@@ -156,8 +156,11 @@ static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* 
   k->qC.table.run(k->sA.p, 3 + L.ti_cnt, nullptr, k->d_out.p, st);                                           // A
   k->qC.table.run(k->qC.scalars.p, k->qC.table.n, nullptr, k->d_out.p + ZK_G1_OUT + ZK_G2_OUT, st);         // C
   k->qB.table.run(k->qB.scalars.p, k->qB.table.n, nullptr, k->d_out.p + ZK_G1_OUT, st);                     // B
+  // all three accumulations are enqueued; the G2 tail runs on the auxiliary stream next to the G1 tail
+  cudaStream_t aux = fork_aux(st);
+  k->qB.table.join(aux);
   k->qC.table.join(st);
-  k->qB.table.join(st);
+  join_aux(st);
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_GROTH16_PROOF_OUT, cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaMemcpyAsync(fl, flag, sizeof(fl), cudaMemcpyDeviceToHost, st));
@@ -425,8 +428,10 @@ int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* s
   auto run2 = [&](int slot, uint8_t* out) { k->q2.table.run(at2(slot), k->cnt2[slot], nullptr, out, st, k->first2[slot]); };
   run1(0, o_vv); run1(1, o_yy); run1(5, o_h); run1(2, o_vav); run1(3, o_yay); run1(4, o_bvwy);
   run2(0, o_ww); run2(1, o_waw);
-  k->q1.table.join(st);   // one batched tail for the six G1 elements
-  k->q2.table.join(st);   // one for the two G2 elements
+  cudaStream_t aux = fork_aux(st);
+  k->q2.table.join(aux);  // one batched tail for the two G2 elements, next to ...
+  k->q1.table.join(st);   // ... the one for the six G1 elements
+  join_aux(st);
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_PINOCCHIO_PROOF_OUT, cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaMemcpyAsync(fl, q.flag.p, sizeof(fl), cudaMemcpyDeviceToHost, st));

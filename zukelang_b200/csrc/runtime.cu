@@ -9,6 +9,8 @@ namespace zk {
 
 static thread_local std::string g_error;
 static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_aux_stream = nullptr;
+static cudaEvent_t g_fork = nullptr, g_join = nullptr;
 static bool g_init = false;
 static int g_sm_count = 0;
 static std::mutex g_mu;
@@ -18,6 +20,17 @@ static uint64_t g_next_handle = 1;
 void set_error(const std::string& s) { g_error = s; }
 const std::string& last_error() { return g_error; }
 cudaStream_t default_stream() { return g_stream; }
+// Runs `on_aux(aux)` on the auxiliary stream, ordered after everything already enqueued on `st`; a
+// later join_aux(st) makes `st` wait for it.  Used to finish the G2 tail next to the G1 tail.
+cudaStream_t fork_aux(cudaStream_t st) {
+  ZK_CUDA(cudaEventRecord(g_fork, st));
+  ZK_CUDA(cudaStreamWaitEvent(g_aux_stream, g_fork, 0));
+  return g_aux_stream;
+}
+void join_aux(cudaStream_t st) {
+  ZK_CUDA(cudaEventRecord(g_join, g_aux_stream));
+  ZK_CUDA(cudaStreamWaitEvent(st, g_join, 0));
+}
 int sm_count() { return g_sm_count; }
 
 int env_int(const char* name, int dflt) {
@@ -66,7 +79,12 @@ int zk_init(int device) {
     if (prop.major < 10)
       throw zk::Error{ZK_ECUDA, std::string("device ") + prop.name + " is not sm_100-class; libzkb200 is built for sm_100a only"};
     zk::g_sm_count = prop.multiProcessorCount;
-    if (!zk::g_stream) ZK_CUDA(cudaStreamCreateWithFlags(&zk::g_stream, cudaStreamNonBlocking));
+    if (!zk::g_stream) {
+      ZK_CUDA(cudaStreamCreateWithFlags(&zk::g_stream, cudaStreamNonBlocking));
+      ZK_CUDA(cudaStreamCreateWithFlags(&zk::g_aux_stream, cudaStreamNonBlocking));
+      ZK_CUDA(cudaEventCreateWithFlags(&zk::g_fork, cudaEventDisableTiming));
+      ZK_CUDA(cudaEventCreateWithFlags(&zk::g_join, cudaEventDisableTiming));
+    }
     zk::g_init = true;
   } catch (const zk::Error& e) {
     zk::set_error(e.msg);
@@ -82,7 +100,11 @@ int zk_shutdown(void) {
   }
   if (zk::g_stream) {
     cudaStreamDestroy(zk::g_stream);
+    cudaStreamDestroy(zk::g_aux_stream);
+    cudaEventDestroy(zk::g_fork);
+    cudaEventDestroy(zk::g_join);
     zk::g_stream = nullptr;
+    zk::g_aux_stream = nullptr;
   }
   zk::g_init = false;
   return ZK_OK;
