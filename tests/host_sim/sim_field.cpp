@@ -22,6 +22,7 @@ static void binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 6: r = x.inverse(); break;
     case 7: r = x.dbl(); break;
     case 8: r = x.inverse_fermat(); break;
+    case 9: r = x.sqr(); break;
     default: r = F::zero();
   }
   memcpy(out, r.v, sizeof(r.v));

@@ -41,7 +41,8 @@ def test_montgomery_limb_algorithms(sim, which, mod, n):
     rng = random.Random(5)
     Rm = 1 << (32 * n)
     Ri = pow(Rm, -1, mod)
-    vals = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, Rm % mod] + [rng.randrange(mod) for _ in range(150)]
+    vals = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, Rm % mod, (1 << (32 * n - 3)) % mod, mod - (1 << 200)] \
+        + [rng.randrange(mod) for _ in range(400)]
     for i, a in enumerate(vals):
         b = vals[(i * 7 + 3) % len(vals)]
         assert _field(fn, n, 0, a, b) == a * b * Ri % mod
@@ -50,6 +51,7 @@ def test_montgomery_limb_algorithms(sim, which, mod, n):
         assert _field(fn, n, 3, a) == (-a) % mod
         assert _field(fn, n, 4, a) == a * Rm % mod
         assert _field(fn, n, 5, a) == a * Ri % mod
+        assert _field(fn, n, 9, a) == a * a * Ri % mod               # dedicated squaring
     for a in vals[:40]:
         exp = (pow(a, -1, mod) * Rm % mod) if a else 0
         assert _field(fn, n, 6, a * Rm % mod) == exp                 # binary extended Euclid

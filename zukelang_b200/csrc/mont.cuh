@@ -160,7 +160,71 @@ struct alignas(16) Mont {
     final_sub(r, 0);
     return r;
   }
-  ZK_HD Mont sqr() const { return *this * *this; }
+  // ---- Montgomery square ---------------------------------------------------------
+  // a^2 = sum_i a_i * e^(i) * 2^(32 i) with e^(i) = (0, .., 0, a_i, 2 a_{i+1}, .., 2 a_{N-1}): row i of
+  // the CIOS loop only multiplies the limbs j >= i, 78 partial products for N = 12 instead of 144
+  // (needs 2a + p < 2^(32 N): true for Fp; Fr, one bit short, keeps the plain product).  Limbs of the row
+  // operand below `start` are zero: the odd-aligned chain just shifts there (carry adds on the ALU
+  // pipe) and the even-aligned chain starts at the first non-zero limb.
+  static ZK_HD void sqr_row(uint32_t* even, uint32_t* odd, const uint32_t* e, uint32_t bi, int start) {
+    even[0] = ptx::add_cc(even[0], odd[1]);
+    ZK_UNROLL for (int j = 0; j < N - 2; j += 2) {
+      if (j + 1 >= start) {
+        odd[j] = ptx::madc_lo_cc(e[j + 1], bi, odd[j + 2]);
+        odd[j + 1] = ptx::madc_hi_cc(e[j + 1], bi, odd[j + 3]);
+      } else {
+        odd[j] = ptx::addc_cc(odd[j + 2], 0);
+        odd[j + 1] = ptx::addc_cc(odd[j + 3], 0);
+      }
+    }
+    odd[N - 2] = ptx::madc_lo_cc(e[N - 1], bi, 0);
+    odd[N - 1] = ptx::madc_hi(e[N - 1], bi, 0);
+    const int fe = start + (start & 1);  // first even limb >= start
+    if (fe < N) {
+      even[fe] = ptx::mad_lo_cc(e[fe], bi, even[fe]);
+      even[fe + 1] = ptx::madc_hi_cc(e[fe], bi, even[fe + 1]);
+      ZK_UNROLL for (int j = 0; j < N; j += 2) {
+        if (j > fe) {
+          even[j] = ptx::madc_lo_cc(e[j], bi, even[j]);
+          even[j + 1] = ptx::madc_hi_cc(e[j], bi, even[j + 1]);
+        }
+      }
+      odd[N - 1] = ptx::addc(odd[N - 1], 0);
+    }
+    reduce_row(even, odd);
+  }
+  ZK_HD Mont sqr() const {
+    // (valid only when 2a + p fits the N-limb accumulator: Fp has 3 spare bits, Fr has one)
+    if (!P::FAST_SQR) return *this * *this;
+    // d = 2a limb-wise with the carries between limbs; row i uses e = (.., a_i, a_{i+1} << 1, d_{i+2}, ..):
+    // the bit that 2 a_i pushes into limb i+1 belongs to the diagonal term, not to row i's cross terms
+    uint32_t d[N], e[N], ev[N], od[N];
+    d[0] = v[0] << 1;
+    ZK_UNROLL for (int i = 1; i < N; i++) d[i] = (v[i] << 1) | (v[i - 1] >> 31);
+    ZK_UNROLL for (int j = 0; j < N; j++) e[j] = d[j];
+    e[0] = v[0];
+    e[1] = v[1] << 1;
+    mul_n<N>(ev, e, v[0]);
+    mul_n<N>(od, e + 1, v[0]);
+    reduce_row(ev, od);
+    ZK_UNROLL for (int i = 1; i < N; i += 2) {
+      e[i] = v[i];
+      if (i + 1 < N) e[i + 1] = v[i + 1] << 1;
+      sqr_row(od, ev, e, v[i], i);
+      if (i + 1 < N) {
+        e[i + 1] = v[i + 1];
+        if (i + 2 < N) e[i + 2] = v[i + 2] << 1;
+        sqr_row(ev, od, e, v[i + 1], i + 1);
+        if (i + 2 < N) e[i + 2] = d[i + 2];   // restored: the next row patches it again as its own a_i
+      }
+    }
+    Mont r;
+    r.v[0] = ptx::add_cc(ev[0], od[1]);
+    ZK_UNROLL for (int i = 1; i < N - 1; i++) r.v[i] = ptx::addc_cc(ev[i], od[i + 1]);
+    r.v[N - 1] = ptx::addc(ev[N - 1], 0);
+    final_sub(r, 0);
+    return r;
+  }
   // out-of-line product for code that is not throughput critical (keeps kernels small)
   static ZK_NI Mont mul_call(const Mont& a, const Mont& b) { return a * b; }
 
