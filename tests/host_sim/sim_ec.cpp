@@ -16,6 +16,10 @@ static void ec_op(int op, const uint32_t* a, const uint32_t* b, const uint32_t* 
     case 2: r = A.dbl(); break;
     case 3: r = scalar_mul(A, k); break;
     case 4: r = XYZZ<F>::dbl_affine(Q); break;
+    case 5:   // Fp only (Mont::mul2)
+      r = A;
+      if constexpr (sizeof(F) == sizeof(Fp)) r.madd_paired(Q); else r.madd(Q);
+      break;
   }
   Affine<F> aff = r.to_affine();
   memcpy(out, &aff, sizeof(aff));

@@ -116,9 +116,12 @@ def test_xyzz_formulas(sim, G):
         for q in pts:
             z = rng.randrange(1, P)
             assert _ec(sim, G, 0, _enc_xyzz(G, p, z, w), _enc_aff(G, q, w)) == G.add(p, q)
+            assert _ec(sim, G, 5, _enc_xyzz(G, p, z, w), _enc_aff(G, q, w)) == G.add(p, q)   # paired products
             assert _ec(sim, G, 1, _enc_xyzz(G, p, z, w), _enc_xyzz(G, q, z + 3, w)) == G.add(p, q)
         z = rng.randrange(1, P)
         assert _ec(sim, G, 0, _enc_xyzz(G, p, z, w), _enc_aff(G, p, w)) == G.add(p, p)          # P + P
+        assert _ec(sim, G, 5, _enc_xyzz(G, p, z, w), _enc_aff(G, p, w)) == G.add(p, p)
+        assert _ec(sim, G, 5, _enc_xyzz(G, p, z, w), _enc_aff(G, G.neg(p), w)) is None
         assert _ec(sim, G, 0, _enc_xyzz(G, p, z, w), _enc_aff(G, G.neg(p), w)) is None           # P - P
         assert _ec(sim, G, 1, _enc_xyzz(G, p, z, w), _enc_xyzz(G, G.neg(p), z + 5, w)) is None
         assert _ec(sim, G, 2, _enc_xyzz(G, p, z, w), []) == G.add(p, p)

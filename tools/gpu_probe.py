@@ -32,9 +32,9 @@ def words_to_ints(w):
 
 
 def microbench(zk):
-    names = {0: "mad.lo.u32", 1: "mad.cc chain", 2: "mad.wide.u32", 3: "Fp mul", 4: "Fr mul", 5: "G1 madd", 6: "G1 madd call/4", 7: "G1 madd inline/4", 8: "G1 madd call/5", 9: "G1 madd call/3"}
-    iters = {0: 4096, 1: 4096, 2: 4096, 3: 256, 4: 512, 5: 64, 6: 64, 7: 64, 8: 64, 9: 64}
-    for kind in range(10):
+    names = {0: "mad.lo.u32", 1: "mad.cc chain", 2: "mad.wide.u32", 3: "Fp mul", 4: "Fr mul", 5: "G1 madd", 6: "G1 madd call/4", 7: "G1 madd inline/4", 8: "G1 madd call/5", 9: "G1 madd call/3", 10: "G1 madd paired/4", 11: "G1 madd paired/3", 12: "G1 madd paired/2"}
+    iters = {0: 4096, 1: 4096, 2: 4096, 3: 256, 4: 512, 5: 64, 6: 64, 7: 64, 8: 64, 9: 64, 10: 64, 11: 64, 12: 64}
+    for kind in range(13):
         ops, ms = ctypes.c_double(), ctypes.c_double()
         best = 0.0
         for _ in range(3):

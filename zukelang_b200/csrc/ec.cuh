@@ -16,10 +16,22 @@ typedef Mont<FrParams> Fr;
 
 // The one out-of-line Fp product: arguments and result stay in registers under the device ABI.
 // Used by Fp2 and FpCall, where fully inlined formulas would be tens of kilobytes of code.
+struct FpPair { Fp lo, hi; };
 #ifndef ZK_HOST_SIM
 static __device__ __noinline__ Fp fp_mul_outofline(Fp a, Fp b) { return a * b; }
+// two independent products with interleaved rows (Mont::mul2), out of line
+static __device__ __noinline__ FpPair fp_mul2_outofline(Fp a, Fp b, Fp c, Fp d) {
+  FpPair r;
+  Fp::mul2(a, b, c, d, r.lo, r.hi);
+  return r;
+}
 #else
 static inline Fp fp_mul_outofline(Fp a, Fp b) { return a * b; }
+static inline FpPair fp_mul2_outofline(Fp a, Fp b, Fp c, Fp d) {
+  FpPair r;
+  Fp::mul2(a, b, c, d, r.lo, r.hi);
+  return r;
+}
 #endif
 
 // -------------------------------------------------------------------------
@@ -38,17 +50,16 @@ struct Fp2 {
   ZK_HD Fp2 dbl() const { return Fp2{c0.dbl(), c1.dbl()}; }
   // Karatsuba: 3 Fp products
   friend ZK_HD Fp2 operator*(const Fp2& a, const Fp2& b) {
-    Fp t0 = fp_mul_outofline(a.c0, b.c0);
-    Fp t1 = fp_mul_outofline(a.c1, b.c1);
+    FpPair t = fp_mul2_outofline(a.c0, b.c0, a.c1, b.c1);
     Fp t2 = fp_mul_outofline(a.c0 + a.c1, b.c0 + b.c1);
-    return Fp2{t0 - t1, t2 - t0 - t1};
+    return Fp2{t.lo - t.hi, t2 - t.lo - t.hi};
   }
   // (c0 + c1 u)^2 = (c0 + c1)(c0 - c1) + 2 c0 c1 u : 2 Fp products
   ZK_HD Fp2 sqr() const {
     Fp s = c0 + c1;
     Fp d = c0 - c1;
-    Fp m = fp_mul_outofline(c0, c1);
-    return Fp2{fp_mul_outofline(s, d), m.dbl()};
+    FpPair t = fp_mul2_outofline(c0, c1, s, d);
+    return Fp2{t.hi, t.lo.dbl()};
   }
   ZK_NI Fp2 inverse() const {
     Fp n = Fp::mul_call(c0, c0) + Fp::mul_call(c1, c1);
@@ -135,6 +146,34 @@ struct XYZZ {
     r.ZZ = V * ZZ;
     r.ZZZ = W * ZZZ;
     return r;
+  }
+
+  // madd with the independent products issued in interleaved pairs (Mont::mul2); Fp only
+  ZK_HD void madd_paired(const Affine<F>& p) {
+    if (p.is_inf()) return;
+    if (is_inf()) {
+      X = p.x; Y = p.y; ZZ = F::one(); ZZZ = F::one();
+      return;
+    }
+    F U2, S2;
+    F::mul2(p.x, ZZ, p.y, ZZZ, U2, S2);
+    F Pd = U2 - X;
+    F Rd = S2 - Y;
+    if (Pd.is_zero()) {
+      if (Rd.is_zero()) *this = dbl_affine(p);
+      else *this = inf();
+      return;
+    }
+    F PP = Pd.sqr();
+    F RR = Rd.sqr();
+    F PPP, Q;
+    F::mul2(Pd, PP, X, PP, PPP, Q);
+    F X3 = RR - PPP - Q.dbl();
+    F t1, t2;
+    F::mul2(Rd, Q - X3, Y, PPP, t1, t2);
+    F::mul2(ZZ, PP, ZZZ, PPP, ZZ, ZZZ);
+    Y = t1 - t2;
+    X = X3;
   }
 
   // this += affine p   — madd-2008-s, with the exceptional cases handled

@@ -108,6 +108,15 @@ __global__ void __launch_bounds__(128, MINB) k_mb_madd_var(uint32_t* out, int it
   if (w[0] == 0x12345678u && w[13] == 0x9abcdef0u) out[0] = w[26];
 }
 
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_mb_madd_paired(uint32_t* out, int iters) {
+  G1Affine g = G1Traits::generator();
+  G1XYZZ acc = G1XYZZ::dbl_affine(g);
+  for (int i = 0; i < (int)(threadIdx.x & 3); i++) acc = acc.dbl();
+  for (int it = 0; it < iters; it++) acc.madd_paired(g);
+  if (acc.X.v[0] == 0x12345678u && acc.Y.v[1] == 0x9abcdef0u) out[0] = acc.ZZ.v[2];
+}
+
 // ---- device field-op test hook ----------------------------------------------------
 template <class F>
 __global__ void k_test_field_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, uint32_t n) {
@@ -156,6 +165,9 @@ int zk_bench_intpipe(int kind, int iters, double* ops_per_s, double* elapsed_ms)
       case 7: k_mb_madd_var<Fp, 4><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
       case 8: k_mb_madd_var<FpCall, 5><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
       case 9: k_mb_madd_var<FpCall, 3><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
+      case 10: k_mb_madd_paired<4><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
+      case 11: k_mb_madd_paired<3><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
+      case 12: k_mb_madd_paired<2><<<blocks, 128, 0, st>>>(d_out.p, it); ops = (double)blocks * 128 * it; break;
       default: throw Error{ZK_EARG, "bench_intpipe: unknown kind"};
     }
   };

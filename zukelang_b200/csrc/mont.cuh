@@ -160,6 +160,36 @@ struct alignas(16) Mont {
     final_sub(r, 0);
     return r;
   }
+  // Two independent products with their CIOS rows interleaved: r1 = a b, r2 = c d.  Each product
+  // is a serial chain of rows (row i+1 needs row i's accumulator); issuing the rows of two products
+  // alternately gives the scheduler two independent chains to overlap, which hides the dependent-
+  // issue latency of IMAD.WIDE.X at low occupancy.
+  static ZK_HD void mul2(const Mont& a, const Mont& b, const Mont& c, const Mont& d, Mont& r1, Mont& r2) {
+    uint32_t e1[N], o1[N], e2[N], o2[N];
+    mul_n<N>(e1, a.v, b.v[0]);
+    mul_n<N>(e2, c.v, d.v[0]);
+    mul_n<N>(o1, a.v + 1, b.v[0]);
+    mul_n<N>(o2, c.v + 1, d.v[0]);
+    reduce_row(e1, o1);
+    reduce_row(e2, o2);
+    ZK_UNROLL for (int i = 1; i < N; i += 2) {
+      mad_row(o1, e1, a.v, b.v[i]);
+      mad_row(o2, e2, c.v, d.v[i]);
+      if (i + 1 < N) {
+        mad_row(e1, o1, a.v, b.v[i + 1]);
+        mad_row(e2, o2, c.v, d.v[i + 1]);
+      }
+    }
+    r1.v[0] = ptx::add_cc(e1[0], o1[1]);
+    ZK_UNROLL for (int i = 1; i < N - 1; i++) r1.v[i] = ptx::addc_cc(e1[i], o1[i + 1]);
+    r1.v[N - 1] = ptx::addc(e1[N - 1], 0);
+    r2.v[0] = ptx::add_cc(e2[0], o2[1]);
+    ZK_UNROLL for (int i = 1; i < N - 1; i++) r2.v[i] = ptx::addc_cc(e2[i], o2[i + 1]);
+    r2.v[N - 1] = ptx::addc(e2[N - 1], 0);
+    final_sub(r1, 0);
+    final_sub(r2, 0);
+  }
+
   // ---- Montgomery square ---------------------------------------------------------
   // a^2 = sum_i a_i * e^(i) * 2^(32 i) with e^(i) = (0, .., 0, a_i, 2 a_{i+1}, .., 2 a_{N-1}): row i of
   // the CIOS loop only multiplies the limbs j >= i, 78 partial products for N = 12 instead of 144

@@ -185,8 +185,9 @@ k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __rest
 // k_fix_partials adds them up.  Bases are gathered with 128-bit loads, the next base is fetched
 // while the current one is added.
 // MINB = resident blocks per SM the register allocation is capped for; PREFETCH = fetch the
-// next base while adding the current one (costs 24 registers).
-template <class F, int MINB, bool PREFETCH>
+// next base while adding the current one (costs 24 registers); PAIRED = mixed add with its
+// independent products issued as interleaved pairs (Fp only; wants the registers of MINB = 2).
+template <class F, int MINB, bool PREFETCH, bool PAIRED = false>
 __global__ void __launch_bounds__(128, MINB)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums, XYZZ<F>* __restrict__ partial,
@@ -236,7 +237,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
       e = entries[k];
       cur = load_vec(&bases[e & 0x7fffffffu]);
       if (e >> 31) cur.y = cur.y.neg();
-      acc.madd(cur);
+      if constexpr (PAIRED) acc.madd_paired(cur); else acc.madd(cur);
     }
   }
   // last piece: bucket b from seg_start to e1
@@ -501,7 +502,8 @@ struct BaseTable {
   // finishes them with ONE batched launch sequence on the caller's stream (flush / join).
   DevBuf<XYZZ<F>> bucket_sums, partial, chunk_out, tree_tmp, window_sums;   // MSM_QUEUE slots each (partial: 1)
   uint32_t acc_blocks = 0;   // persistent grid of k_accumulate: resident blocks per SM x SMs
-  int acc_variant = 0;       // 0: 3 blocks/SM + prefetch, 1: 4 no prefetch, 2: 4 + prefetch, 3: 5 no prefetch
+  int acc_variant = 0;       // ZKB200_ACC_VARIANT: 8 (default, G1) = paired products, 2 blocks/SM, 254 registers;
+                             // 1 = 4 blocks/SM; 0/2/3 = older shapes; 4/5 = G2 (255 registers)
   int queued = 0;
   TailOutputs<F> outs{};
   // batched-affine accumulation (msm_ba.cuh), selected by ZKB200_BATCHED_AFFINE

@@ -8,7 +8,7 @@
 #define ZK_BATCHED_AFFINE_DEFAULT 0
 #endif
 #ifndef ZK_ACC_VARIANT_DEFAULT
-#define ZK_ACC_VARIANT_DEFAULT 1
+#define ZK_ACC_VARIANT_DEFAULT 8
 #endif
 
 namespace zk {
@@ -106,6 +106,8 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
     acc_variant = env_int(sizeof(F) > 48 ? "ZKB200_ACC_VARIANT_G2" : "ZKB200_ACC_VARIANT", sizeof(F) > 48 ? 4 : ZK_ACC_VARIANT_DEFAULT);
     switch (acc_variant) {
       case 4: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); break;
+      case 8: if constexpr (sizeof(F) == sizeof(Fp)) { ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false, true>, 128, 0)); } else { acc_variant = 4; ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); } break;
+      case 9: if constexpr (sizeof(F) == sizeof(Fp)) { ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 3, false, true>, 128, 0)); } else { acc_variant = 4; ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); } break;
       case 5: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 1, false>, 128, 0)); break;
       case 1: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, false>, 128, 0)); break;
       case 2: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, true>, 128, 0)); break;
@@ -201,6 +203,8 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   if (grid < 1) grid = 1;
   switch (acc_variant) {
     case 4: k_accumulate<F, 2, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
+    case 8: if constexpr (sizeof(F) == sizeof(Fp)) k_accumulate<F, 2, false, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
+    case 9: if constexpr (sizeof(F) == sizeof(Fp)) k_accumulate<F, 3, false, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
     case 5: k_accumulate<F, 1, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
     case 1: k_accumulate<F, 4, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
     case 2: k_accumulate<F, 4, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
