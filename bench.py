@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 MAC32_PER_POINT = 48_000          # 16 windows x 3 000 MAC32 (G1 XYZZ mixed add)
 LOG_N = 20
-NCU_DRAM_BYTES_PER_LAUNCH = 3_128_247_616   # k_accumulate, 2^20 points, c = 17 (profiles/r01_ncu_accumulate.md)
+NCU_DRAM_BYTES_PER_LAUNCH = 3_046_744_160   # k_accumulate, 2^20 points, c = 17 (profiles/r01_ncu_accumulate.md)
 SEED_SCALARS, SEED_BASES = 0x5A554B45, 0x42415345
 
 
