@@ -502,8 +502,8 @@ struct BaseTable {
   // finishes them with ONE batched launch sequence on the caller's stream (flush / join).
   DevBuf<XYZZ<F>> bucket_sums, partial, chunk_out, tree_tmp, window_sums;   // MSM_QUEUE slots each (partial: 1)
   uint32_t acc_blocks = 0;   // persistent grid of k_accumulate: resident blocks per SM x SMs
-  int acc_variant = 0;       // ZKB200_ACC_VARIANT: 8 (default, G1) = paired products, 2 blocks/SM, 254 registers;
-                             // 1 = 4 blocks/SM; 0/2/3 = older shapes; 4/5 = G2 (255 registers)
+  int acc_variant = 0;       // ZKB200_ACC_VARIANT[_G2]: 8 (G1 default) paired products, 254 registers, 2 blocks/SM;
+                             // 1 plain, 128 registers, 4 blocks/SM; 4 (G2 default) plain, 255 registers
   int queued = 0;
   TailOutputs<F> outs{};
   // batched-affine accumulation (msm_ba.cuh), selected by ZKB200_BATCHED_AFFINE

@@ -104,15 +104,16 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   {
     int per_sm = 0;
     acc_variant = env_int(sizeof(F) > 48 ? "ZKB200_ACC_VARIANT_G2" : "ZKB200_ACC_VARIANT", sizeof(F) > 48 ? 4 : ZK_ACC_VARIANT_DEFAULT);
+    // 8 (G1 default): paired products, 254 registers, 2 blocks/SM; 1: plain mixed add at 128
+    // registers, 4 blocks/SM; 4 (G2 default): plain mixed add at 255 registers, 2 blocks/SM
+    if (acc_variant == 8 && sizeof(F) != sizeof(Fp)) acc_variant = 4;
+    if (acc_variant != 1 && acc_variant != 4 && acc_variant != 8) acc_variant = sizeof(F) > 48 ? 4 : 8;
     switch (acc_variant) {
-      case 4: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); break;
-      case 8: if constexpr (sizeof(F) == sizeof(Fp)) { ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false, true>, 128, 0)); } else { acc_variant = 4; ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); } break;
-      case 9: if constexpr (sizeof(F) == sizeof(Fp)) { ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 3, false, true>, 128, 0)); } else { acc_variant = 4; ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); } break;
-      case 5: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 1, false>, 128, 0)); break;
       case 1: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, false>, 128, 0)); break;
-      case 2: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, true>, 128, 0)); break;
-      case 3: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 5, false>, 128, 0)); break;
-      default: acc_variant = 0; ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 3, true>, 128, 0));
+      case 4: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); break;
+      default:
+        if constexpr (sizeof(F) == sizeof(Fp))
+          ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false, true>, 128, 0));
     }
     if (per_sm < 1) per_sm = 1;
     acc_blocks = (uint32_t)per_sm * (uint32_t)sm_count();
@@ -202,14 +203,11 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   if (grid > acc_blocks) grid = acc_blocks;
   if (grid < 1) grid = 1;
   switch (acc_variant) {
-    case 4: k_accumulate<F, 2, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
-    case 8: if constexpr (sizeof(F) == sizeof(Fp)) k_accumulate<F, 2, false, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
-    case 9: if constexpr (sizeof(F) == sizeof(Fp)) k_accumulate<F, 3, false, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
-    case 5: k_accumulate<F, 1, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
     case 1: k_accumulate<F, 4, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
-    case 2: k_accumulate<F, 4, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
-    case 3: k_accumulate<F, 5, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
-    default: k_accumulate<F, 3, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb);
+    case 4: k_accumulate<F, 2, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
+    default:
+      if constexpr (sizeof(F) == sizeof(Fp))
+        k_accumulate<F, 2, false, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb);
   }
   ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));
   k_fix_partials<F><<<cdiv(nb, 128), 128, 0, st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p, heavy.p + 1);
