@@ -1,0 +1,41 @@
+"""Contract checks that need no GPU: the C header is valid C (and C++), and the reference arm of
+bench.py prints exactly one JSON line with the agreed keys."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_is_plain_c_and_cxx(tmp_path):
+    hdr = os.path.join(ROOT, "include", "zkb200.h")
+    c = tmp_path / "t.c"
+    c.write_text('#include "zkb200.h"\nint main(void) { zk_groth16_pkey k; (void)k; return ZK_G1_OUT + ZK_PINOCCHIO_PROOF_OUT > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.dirname(hdr), str(c)])
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "zkb200.h"\nint main() { zk_pinocchio_pkey k{}; return k.n == 0 ? 0 : 1; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), str(cpp)])
+
+
+def test_reference_arm_prints_one_contract_line():
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
+                          "--steps", "1", "--warmup", "3"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "Mpts/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+    # other ranks of a torchrun job stay silent and exit 0
+    env["RANK"] = "1"
+    env["WORLD_SIZE"] = "2"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "3"], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
