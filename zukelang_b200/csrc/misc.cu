@@ -225,8 +225,15 @@ int zk_table_pipeline(uint64_t handle, int enable) {
   using namespace zk;
   HandleBase* hb = lookup_handle(handle, 0);
   ZK_REQUIRE(hb->kind == 1 || hb->kind == 2, ZK_EARG, "table_pipeline: not a table handle");
-  if (hb->kind == 1) static_cast<TableHandle<G1Traits>*>(hb)->table.pipelined = enable != 0;
-  else static_cast<TableHandle<G2Traits>*>(hb)->table.pipelined = enable != 0;
+  if (hb->kind == 1) {
+    auto& t = static_cast<TableHandle<G1Traits>*>(hb)->table;
+    if (!enable && t.queued) { ZK_CUDA(cudaDeviceSynchronize()); t.join(default_stream()); ZK_CUDA(cudaStreamSynchronize(default_stream())); }
+    t.set_pipelined(enable != 0);
+  } else {
+    auto& t = static_cast<TableHandle<G2Traits>*>(hb)->table;
+    if (!enable && t.queued) { ZK_CUDA(cudaDeviceSynchronize()); t.join(default_stream()); ZK_CUDA(cudaStreamSynchronize(default_stream())); }
+    t.set_pipelined(enable != 0);
+  }
   ZK_API_END
 }
 

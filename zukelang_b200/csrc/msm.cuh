@@ -505,6 +505,7 @@ struct BaseTable {
   int acc_variant = 0;       // ZKB200_ACC_VARIANT[_G2]: 8 (G1 default) paired products, 254 registers, 2 blocks/SM;
                              // 1 plain, 128 registers, 4 blocks/SM; 4 (G2 default) plain, 255 registers
   int queued = 0;
+  int queue_cap = 0;         // bucket buffers currently allocated (1 unless pipelined)
   TailOutputs<F> outs{};
   // batched-affine accumulation (msm_ba.cuh), selected by ZKB200_BATCHED_AFFINE
   bool use_ba = false;
@@ -524,6 +525,9 @@ struct BaseTable {
            uint32_t first = 0);
   // finish every queued MSM on `st` (batched tail); results are valid in stream order afterwards
   void join(cudaStream_t st);
+  // pipelined = queue up to MSM_QUEUE tails (allocates that many bucket buffers on first use)
+  void set_pipelined(bool on);
+  void ensure_queue(int slots);
   // stage timing (bench.py's roofline leg): when `profile` is set, run() brackets its stages with
   // CUDA events; stage_ms() reads them after the streams have drained.
   // stages: 0 digits+scan+scatter, 1 accumulate (+ partial fix-up), 2 bucket reduce, 3 combine+finalize

@@ -78,7 +78,7 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
   }
   ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st));
   const bool was = h->table.pipelined;
-  h->table.pipelined = true;
+  h->table.set_pipelined(true);
   for (size_t i = 0; i < count; i++) {
     int b = (int)(i & 1);
     ZK_REQUIRE(scalars[i], ZK_EARG, "msm_batch: null scalar vector");
@@ -91,7 +91,7 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
     ZK_CUDA(cudaEventRecord(consumed[b], st));
   }
   h->table.join(st);
-  h->table.pipelined = was;
+  h->table.set_pipelined(was);
   int err = 0;
   ZK_CUDA(cudaMemcpyAsync(out, d_outs.p, count * (T::RAW + T::COMP), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));

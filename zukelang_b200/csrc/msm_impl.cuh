@@ -121,12 +121,12 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   uint32_t cpw = cfg.B / cfg.L;
   heavy.alloc((size_t)acc_blocks * 128 / 4 + 2);
   partial.alloc(2 * (size_t)acc_blocks * 128);
-  bucket_sums.alloc((size_t)MSM_QUEUE * nb);
-  chunk_out.alloc((size_t)MSM_QUEUE * cfg.nwb * cpw);
-  tree_tmp.alloc((size_t)MSM_QUEUE * cfg.nwb * cdiv(cpw, TAIL_THREADS) + 1);
-  window_sums.alloc((size_t)MSM_QUEUE * (cfg.nwb + 1));
+  (void)cpw;
   queued = 0;
-  pipelined = env_int("ZKB200_PIPELINE", 0) != 0;
+  queue_cap = 0;
+  pipelined = false;
+  ensure_queue(1);
+  if (env_int("ZKB200_PIPELINE", 0) != 0) set_pipelined(true);
   use_ba = env_int("ZKB200_BATCHED_AFFINE", ZK_BATCHED_AFFINE_DEFAULT) != 0;
   if (use_ba) {
     uint64_t E = (uint64_t)n * cfg.W;
@@ -156,7 +156,7 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
                        cudaStream_t st, uint32_t first) {
   ZK_REQUIRE(count > 0 && (uint64_t)first + count <= n, ZK_EARG, "scalar range exceeds the base table");
   const uint32_t nb = cfg.nbuckets();
-  if (queued == MSM_QUEUE) join(st);
+  if (queued >= queue_cap) join(st);
   const int slot = queued;
   if (profile && !ev[0])
     for (auto& e : ev) ZK_CUDA(cudaEventCreate(&e));
@@ -224,6 +224,25 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   queued++;
   ZK_CUDA(cudaGetLastError());
   if (!pipelined) join(st);
+}
+
+template <class T>
+void BaseTable<T>::ensure_queue(int slots) {
+  if (slots <= queue_cap) return;
+  ZK_REQUIRE(queued == 0, ZK_EARG, "cannot resize the tail queue while MSMs are queued");
+  const uint32_t nb = cfg.nbuckets();
+  const uint32_t cpw = cfg.B / cfg.L;
+  bucket_sums.alloc((size_t)slots * nb);
+  chunk_out.alloc((size_t)slots * cfg.nwb * cpw);
+  tree_tmp.alloc((size_t)slots * cfg.nwb * cdiv(cpw, TAIL_THREADS) + 1);
+  window_sums.alloc((size_t)slots * (cfg.nwb + 1));
+  queue_cap = slots;
+}
+
+template <class T>
+void BaseTable<T>::set_pipelined(bool on) {
+  if (on) ensure_queue(MSM_QUEUE);
+  pipelined = on;
 }
 
 // Batched tail of every queued MSM: bucket reduction, window combine, affine conversion.
