@@ -84,7 +84,7 @@ int zk_g2_table_msm_batch(uint64_t handle, const uint8_t *const *scalars, size_t
 int zk_g1_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *cuda_stream);
 int zk_g2_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *cuda_stream);
 /* info[0] = window bits c, [1] = windows W, [2] = bucket windows, [3] = buckets per window,
- * [4] = segments, [5] = device bytes, [6] = points, [7] = precomputed */
+ * [4] = 1 (legacy field), [5] = device bytes, [6] = points, [7] = precomputed */
 int zk_table_info(uint64_t handle, uint64_t info[8]);
 /* Pipelining of consecutive *_msm_dev calls on one table.  Each MSM ends in a latency-bound
  * tail (bucket reduction, window combine, affine conversion: ~40 dependent point operations) whose

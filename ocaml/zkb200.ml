@@ -3,44 +3,182 @@
    Keeps the reference's functor signatures: [Curve.S], [Protocol.S],
    [Groth16.Make (C : Curve.S)], [Pinocchio.Make (C)] — only the bodies of the hot functions
    change.  The aliases at the bottom make the README's spelling ([Ecp.Bls12_381],
-   [Protocol.Test]) resolve as well as the real one ([Curve.Bls12_381], [Test.Make]). *)
+   [Protocol.Test]) resolve as well as the real one ([Curve.Bls12_381], [Test.Make]).
+
+   The C side is ocaml/zkb200_stubs.c over include/zkb200.h; tests/test_cpu_contract.py compiles the
+   stubs against that header.  The Python mirror (zukelang_b200/groth16.py, pinocchio.py) is the
+   executable counterpart of this file and is what the parity tests drive. *)
 
 external init : int -> unit = "zkb200_init"
-external g1_msm : bytes -> bytes -> bytes = "zkb200_g1_msm"
-external g2_msm : bytes -> bytes -> bytes = "zkb200_g2_msm"
+external g1_msm : bytes -> bytes -> bytes = "zkb200_g1_msm"        (* 96 n, 32 n -> 144 *)
+external g2_msm : bytes -> bytes -> bytes = "zkb200_g2_msm"        (* 192 n, 32 n -> 288 *)
+external g1_sum : bytes -> bytes = "zkb200_g1_sum"
+external g2_sum : bytes -> bytes = "zkb200_g2_sum"
 external qap_load : bytes -> bytes -> bytes -> bytes -> int -> int -> int64
   = "zkb200_qap_load_bytecode" "zkb200_qap_load_native"
+external qap_free : int64 -> unit = "zkb200_qap_free"
+external groth16_pk_load : int -> int -> int array -> bytes array -> int * int -> int64
+  = "zkb200_groth16_pk_load"
+external pinocchio_pk_load : int -> int -> int array -> bytes array -> int * int -> int64
+  = "zkb200_pinocchio_pk_load"
+external key_free : int64 -> unit = "zkb200_key_free"
 external groth16_prove : int64 -> int64 -> bytes -> bytes -> bytes -> bytes = "zkb200_groth16_prove"
 external pinocchio_prove : int64 -> int64 -> bytes -> bytes -> bytes = "zkb200_pinocchio_prove"
 
 open Zukelang
 
+let cat = Bytes.concat Bytes.empty
+
 (* [Curve.Bls12_381] with the MSM-shaped members of ExtendMap (curve.ml:79-119) rerouted. *)
 module Bls12_381 = struct
   include Curve.Bls12_381
 
-  let fr_bytes (xs : Fr.t list) = Bytes.concat Bytes.empty (List.map Fr.to_bytes xs)
+  let fr_bytes (xs : Fr.t list) = cat (List.map Fr.to_bytes xs)
 
   module G1 = struct
     include Curve.Bls12_381.G1
 
     let msm (pts : t list) (ks : Fr.t list) : t =
-      let bases = Bytes.concat Bytes.empty (List.map to_bytes pts) in
-      of_bytes_exn (Bytes.sub (g1_msm bases (fr_bytes ks)) 0 96)
+      of_bytes_exn (Bytes.sub (g1_msm (cat (List.map to_bytes pts)) (fr_bytes ks)) 0 96)
+
+    (* curve.ml:91 *)
+    let sum_map m f = Var.Map.fold (fun k v acc -> f k v :: acc) m [] |> fun ps ->
+      msm ps (List.map (fun _ -> Fr.one) ps)
 
     (* curve.ml:94-103 *)
     let dot m c =
       if not (Var.Set.equal (Var.Map.domain m) (Var.Map.domain c)) then begin
         prerr_endline "Domain mismatch"; assert false end;
-      let ks = List.map (fun (k, _) -> Var.Infix.(c #! k)) (Var.Map.bindings m) in
-      msm (List.map snd (Var.Map.bindings m)) ks
+      let bs = Var.Map.bindings m in
+      msm (List.map snd bs) (List.map (fun (k, _) -> Var.Infix.(c #! k)) bs)
 
     (* curve.ml:112-118 *)
     let apply_powers (cs : Fr.t Polynomial.t) xis =
       if List.length cs > List.length xis then invalid_arg "apply_powers";
       msm (Misclib.List.take (List.length cs) xis) cs
   end
-  (* G2 is the same with g2_msm / 192-byte points. *)
+
+  module G2 = struct
+    include Curve.Bls12_381.G2
+
+    let msm (pts : t list) (ks : Fr.t list) : t =
+      of_bytes_exn (Bytes.sub (g2_msm (cat (List.map to_bytes pts)) (fr_bytes ks)) 0 192)
+
+    let dot m c =
+      if not (Var.Set.equal (Var.Map.domain m) (Var.Map.domain c)) then begin
+        prerr_endline "Domain mismatch"; assert false end;
+      let bs = Var.Map.bindings m in
+      msm (List.map snd bs) (List.map (fun (k, _) -> Var.Infix.(c #! k)) bs)
+
+    let apply_powers (cs : Fr.t Polynomial.t) xis =
+      if List.length cs > List.length xis then invalid_arg "apply_powers";
+      msm (Misclib.List.take (List.length cs) xis) cs
+  end
+end
+
+(* Device residency of a QAP.t (QAP.ml:11-16): rows in increasing Var order, coefficients lowest
+   degree first, zero padded to n = degree target.  Cached next to the value by the caller. *)
+module Device (C : module type of Bls12_381) = struct
+  open C
+  module QAP = QAP.Make (Fr)
+  module Poly = Fr.Poly
+
+  let keys (q : QAP.t) = List.map fst (Var.Map.bindings q.v)
+
+  let pad n p =
+    let rec go i = function
+      | _ when i = n -> []
+      | [] -> Fr.zero :: go (i + 1) []
+      | c :: cs -> c :: go (i + 1) cs
+    in
+    fr_bytes (go 0 p)
+
+  let qap (q : QAP.t) : int64 =
+    let n = Poly.degree q.target in
+    let flat m = cat (List.map (fun (_, p) -> pad n p) (Var.Map.bindings m)) in
+    qap_load (flat q.v) (flat q.w) (flat q.y) (pad (n + 1) q.target) (List.length (keys q)) n
+
+  let index_of ks k =
+    let rec go i = function [] -> assert false | x :: xs -> if x = k then i else go (i + 1) xs in
+    go 0 ks
+
+  let solution (q : QAP.t) sol = fr_bytes (List.map (fun k -> Var.Infix.(sol #! k)) (keys q))
+end
+
+(* Groth16.Make (C).prove, groth16.ml:235-237, with the body moved to the GPU.  keygen / verify are
+   the reference's own (include Groth16.Make (C)). *)
+module Groth16 (C : module type of Bls12_381) = struct
+  include Groth16.Make (C)
+  open C
+  module D = Device (C)
+
+  let device_key (pk : pkey) (q : qap) : int64 =
+    let ks = D.keys q in
+    let n = Fr.Poly.degree q.target in
+    let mids = Var.Map.bindings pk.ltd_mid in
+    let g1s l = cat (List.map G1.to_bytes l) and g2s l = cat (List.map G2.to_bytes l) in
+    groth16_pk_load n (List.length ks)
+      (Array.of_list (List.map (fun (k, _) -> D.index_of ks k) mids))
+      [| G1.to_bytes pk.a; G1.to_bytes pk.b1; G1.to_bytes pk.d1; G2.to_bytes pk.b2; G2.to_bytes pk.d2;
+         g1s (Misclib.List.take n pk.ti1); g2s (Misclib.List.take n pk.ti2); g1s pk.tiztd;
+         g1s (List.map snd mids) |]
+      (0, 1)
+
+  let prove rng (q : qap) (pk : pkey) sol : proof =
+    let r = Fr.gen rng in                                  (* groth16.ml:124 — r first *)
+    let s = Fr.gen rng in                                  (* groth16.ml:125 *)
+    let hq = D.qap q and hk = device_key pk q in           (* cache these per key in real use *)
+    let out = groth16_prove hk hq (D.solution q sol) (Fr.to_bytes r) (Fr.to_bytes s) in
+    key_free hk; qap_free hq;
+    { a = G1.of_bytes_exn (Bytes.sub out 0 96);
+      b = G2.of_bytes_exn (Bytes.sub out 144 192);
+      c = G1.of_bytes_exn (Bytes.sub out 432 96) }
+end
+
+(* Pinocchio.Make (C).{NonZK, ZK}.prove, pinocchio.ml:536-538 / 559-561. *)
+module Pinocchio (C : module type of Bls12_381) = struct
+  module P = Pinocchio.Make (C)
+  open C
+  module D = Device (C)
+
+  let device_key (pk : P.KeyGen.pkey) (q : P.qap) : int64 =
+    let ks = D.keys q in
+    let n = Fr.Poly.degree q.target in
+    let mid = List.map fst (Var.Map.bindings pk.vv) in
+    let m1 m = cat (List.map (fun (_, p) -> G1.to_bytes p) (Var.Map.bindings m))
+    and m2 m = cat (List.map (fun (_, p) -> G2.to_bytes p) (Var.Map.bindings m)) in
+    pinocchio_pk_load n (List.length ks) (Array.of_list (List.map (D.index_of ks) mid))
+      [| m1 pk.vv; m1 pk.yy; m1 pk.vav; m1 pk.yay; m1 pk.bvwy; m2 pk.ww; m2 pk.waw;
+         cat (List.map G1.to_bytes (Misclib.List.take (n + 1) pk.si)); m1 pk.v_all; m1 pk.w_all;
+         G1.to_bytes G1.one; G1.to_bytes pk.vt; G1.to_bytes pk.yt; G1.to_bytes pk.vavt; G1.to_bytes pk.yayt;
+         G1.to_bytes pk.vbt; G1.to_bytes pk.wbt; G1.to_bytes pk.ybt; G2.to_bytes pk.wt; G2.to_bytes pk.wawt |]
+      (0, 1)
+
+  let unpack out : P.Compute.proof =
+    let g1 o = G1.of_bytes_exn (Bytes.sub out o 96) and g2 o = G2.of_bytes_exn (Bytes.sub out o 192) in
+    (* vv | ww | yy | h | vavv | waww | yayy | bvwy, 144- and 288-byte point results *)
+    { vv = g1 0; ww = g2 144; yy = g1 432; h = g1 576; vavv = g1 720; waww = g2 864; yayy = g1 1152;
+      bvwy = g1 1296 }
+
+  let prove_with d (q : P.qap) pk sol =
+    let hq = D.qap q and hk = device_key pk q in
+    let out = pinocchio_prove hk hq (D.solution q sol) d in
+    key_free hk; qap_free hq;
+    unpack out
+
+  module NonZK = struct
+    include P.NonZK
+    let prove _rng q pk sol = prove_with Bytes.empty q pk sol
+  end
+
+  module ZK = struct
+    include P.ZK
+    let prove rng q pk sol =
+      let dv = Fr.gen rng in                               (* pinocchio.ml:428 *)
+      let dw = Fr.gen rng in                               (* :429 *)
+      let dy = Fr.gen rng in                               (* :430 *)
+      prove_with (fr_bytes [dv; dw; dy]) q pk sol
+  end
 end
 
 module Ecp = struct module Bls12_381 = Bls12_381 end   (* README.md:36-40 spelling *)

@@ -127,6 +127,113 @@ CAMLprim value zkb200_pinocchio_prove(value pk, value qap, value sol, value d) {
   memcpy(Bytes_val(out), res, ZK_PINOCCHIO_PROOF_OUT);
   CAMLreturn(out);
 }
-/* zk_groth16_pk_load / zk_pinocchio_pk_load take a struct of byte arrays: the stub builds the
- * struct from an OCaml record of Bytes in the same way (one dup_bytes per field), omitted here
- * for brevity — see INTEGRATION.md for the field order. */
+/* ---- proving-key upload ---------------------------------------------------------------------
+ * The OCaml side passes the key as an array of Bytes in the field order of the C struct (see
+ * ocaml/zkb200.ml: groth16_key_fields / pinocchio_key_fields) plus the dimensions and mid_index as
+ * an int array; every field is copied before the runtime lock is released. */
+static uint32_t *dup_index(value idx, size_t *len) {
+  size_t n = Wosize_val(idx);
+  uint32_t *p = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+  for (size_t i = 0; i < n; i++) p[i] = (uint32_t)Long_val(Field(idx, i));
+  if (len) *len = n;
+  return p;
+}
+
+/* groth16_pk_load : n:int -> m:int -> mid_index:int array -> fields:bytes array (9) -> shard:(int*int) -> int64
+ * fields = [| a; b1; d1; b2; d2; ti1; ti2; tiztd; ltd_mid |] */
+CAMLprim value zkb200_groth16_pk_load(value n, value m, value mid_index, value fields, value shard) {
+  CAMLparam5(n, m, mid_index, fields, shard);
+  if (Wosize_val(fields) != 9) caml_invalid_argument("zkb200_groth16_pk_load: 9 key fields expected");
+  uint8_t *f[9];
+  for (int i = 0; i < 9; i++) f[i] = dup_bytes(Field(fields, i), NULL);
+  size_t n_mid;
+  uint32_t *idx = dup_index(mid_index, &n_mid);
+  zk_groth16_pkey pk;
+  memset(&pk, 0, sizeof pk);
+  pk.n = (size_t)Long_val(n); pk.m = (size_t)Long_val(m); pk.n_mid = n_mid; pk.n_h = 0; pk.mid_index = idx;
+  pk.a = f[0]; pk.b1 = f[1]; pk.d1 = f[2]; pk.b2 = f[3]; pk.d2 = f[4];
+  pk.ti1 = f[5]; pk.ti2 = f[6]; pk.tiztd = f[7]; pk.ltd_mid = f[8];
+  int si = Int_val(Field(shard, 0)), sc = Int_val(Field(shard, 1));
+  uint64_t h = 0;
+  caml_release_runtime_system();
+  int rc = zk_groth16_pk_load(&pk, si, sc, &h);
+  caml_acquire_runtime_system();
+  for (int i = 0; i < 9; i++) free(f[i]);
+  free(idx);
+  if (rc) zk_raise(rc);
+  CAMLreturn(caml_copy_int64((int64_t)h));
+}
+
+/* pinocchio_pk_load : n -> m -> mid_index -> fields:bytes array (20) -> shard -> int64
+ * fields = [| vv; yy; vav; yay; bvwy; ww; waw; si; v_all; w_all;
+ *             one; vt; yt; vavt; yayt; vbt; wbt; ybt; wt; wawt |] */
+CAMLprim value zkb200_pinocchio_pk_load(value n, value m, value mid_index, value fields, value shard) {
+  CAMLparam5(n, m, mid_index, fields, shard);
+  if (Wosize_val(fields) != 20) caml_invalid_argument("zkb200_pinocchio_pk_load: 20 key fields expected");
+  uint8_t *f[20];
+  for (int i = 0; i < 20; i++) f[i] = dup_bytes(Field(fields, i), NULL);
+  size_t n_mid;
+  uint32_t *idx = dup_index(mid_index, &n_mid);
+  zk_pinocchio_pkey pk;
+  memset(&pk, 0, sizeof pk);
+  pk.n = (size_t)Long_val(n); pk.m = (size_t)Long_val(m); pk.n_mid = n_mid; pk.mid_index = idx;
+  pk.vv = f[0]; pk.yy = f[1]; pk.vav = f[2]; pk.yay = f[3]; pk.bvwy = f[4]; pk.ww = f[5]; pk.waw = f[6];
+  pk.si = f[7]; pk.v_all = f[8]; pk.w_all = f[9]; pk.one = f[10]; pk.vt = f[11]; pk.yt = f[12]; pk.vavt = f[13];
+  pk.yayt = f[14]; pk.vbt = f[15]; pk.wbt = f[16]; pk.ybt = f[17]; pk.wt = f[18]; pk.wawt = f[19];
+  int si = Int_val(Field(shard, 0)), sc = Int_val(Field(shard, 1));
+  uint64_t h = 0;
+  caml_release_runtime_system();
+  int rc = zk_pinocchio_pk_load(&pk, si, sc, &h);
+  caml_acquire_runtime_system();
+  for (int i = 0; i < 20; i++) free(f[i]);
+  free(idx);
+  if (rc) zk_raise(rc);
+  CAMLreturn(caml_copy_int64((int64_t)h));
+}
+
+CAMLprim value zkb200_qap_free(value h) {
+  CAMLparam1(h);
+  int rc = zk_qap_free((uint64_t)Int64_val(h));
+  if (rc) zk_raise(rc);
+  CAMLreturn(Val_unit);
+}
+
+CAMLprim value zkb200_key_free(value h) {
+  CAMLparam1(h);
+  int rc = zk_key_free((uint64_t)Int64_val(h));
+  if (rc) zk_raise(rc);
+  CAMLreturn(Val_unit);
+}
+
+/* g1_sum / g2_sum : bytes (k points, uncompressed) -> bytes (point result) — combining shard partials */
+CAMLprim value zkb200_g1_sum(value pts) {
+  CAMLparam1(pts);
+  CAMLlocal1(out);
+  size_t nb;
+  uint8_t *b = dup_bytes(pts, &nb);
+  uint8_t res[ZK_G1_OUT];
+  caml_release_runtime_system();
+  int rc = zk_g1_sum(b, nb / ZK_G1_RAW, res);
+  caml_acquire_runtime_system();
+  free(b);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(ZK_G1_OUT);
+  memcpy(Bytes_val(out), res, ZK_G1_OUT);
+  CAMLreturn(out);
+}
+
+CAMLprim value zkb200_g2_sum(value pts) {
+  CAMLparam1(pts);
+  CAMLlocal1(out);
+  size_t nb;
+  uint8_t *b = dup_bytes(pts, &nb);
+  uint8_t res[ZK_G2_OUT];
+  caml_release_runtime_system();
+  int rc = zk_g2_sum(b, nb / ZK_G2_RAW, res);
+  caml_acquire_runtime_system();
+  free(b);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(ZK_G2_OUT);
+  memcpy(Bytes_val(out), res, ZK_G2_OUT);
+  CAMLreturn(out);
+}

@@ -39,3 +39,12 @@ def test_reference_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "3"], capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_ocaml_stubs_compile_against_the_c_abi():
+    """ocaml/zkb200_stubs.c is shipped as source (no OCaml toolchain here); compile it against the
+    real include/zkb200.h with stand-in caml/*.h headers so that a signature drift between the stubs
+    and the C ABI is caught on CPU."""
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-fsyntax-only",
+                           "-I", os.path.join(ROOT, "tests", "ocaml_mock"), "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "ocaml", "zkb200_stubs.c")])

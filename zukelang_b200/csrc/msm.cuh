@@ -7,19 +7,21 @@
 // is the same group element, hence the same serialised bytes.
 //
 // Pipeline (all on the caller's stream, no host round trips):
-//   1. k_digits<COUNT>   signed c-bit digits of every scalar -> bucket histogram
-//   2. k_scan_*          exclusive prefix sum of the histogram
-//   3. k_digits<SCATTER> (bucket, point) pairs placed by counting sort
-//   4. k_accumulate      one thread per (bucket, segment): XYZZ += affine base
-//   5. k_reduce_chunks   running-sum reduction of L buckets per thread
-//      k_reduce_tree     per-window tree sum of the chunk results
-//   6. k_horner          window combine (skipped when the table is precomputed)
-//   7. k_finalize        XYZZ -> affine -> uncompressed + compressed bytes
+//   1. k_digits<COUNT>    scalar -> (negate if > (r-1)/2) -> signed c-bit digits -> bucket histogram
+//   2. k_scan_*           exclusive prefix sum of the histogram
+//   3. k_digits<SCATTER>  (bucket, point) pairs placed by counting sort
+//   4. k_accumulate       persistent, exactly balanced: thread t folds slice t of the sorted list
+//                         with XYZZ mixed adds (paired interleaved products, dedicated squares)
+//      k_fix_partials / k_fix_heavy   buckets split over several slices: add up their pieces
+//   5. k_reduce_chunks    running-sum reduction of L buckets per thread        } the latency-bound
+//      k_reduce_tree      per-window tree sum of the chunk results             } tail: deferred and
+//   6. k_combine_finalize window combine (a copy when precomputed), affine     } batched over up to
+//                         conversion, wire bytes                               } 16 queued MSMs
 //
-// A BaseTable built with `precompute` holds 2^(c*w) * P_i for every window w, so
-// all windows share ONE set of 2^(c-1) buckets: the bucket reduction shrinks W
-// times and the window combine disappears, at the price of W times the table
-// bytes — cheap against 180 GB of HBM3e.
+// A BaseTable built with `precompute` holds 2^(c*w) * P_i for every window w, so all windows
+// share ONE set of 2^(c-1) buckets: the bucket reduction shrinks W times and the window combine
+// disappears, at the price of W times the table bytes — cheap against 180 GB of HBM3e.
+// (msm_ba.cuh holds an experimental batched-affine accumulation, off by default.)
 #pragma once
 #include "common.cuh"
 
