@@ -213,6 +213,30 @@ int zk_pinocchio_prove(uint64_t pk, uint64_t qap, const uint8_t *sol, const uint
                        uint8_t proof_out[ZK_PINOCCHIO_PROOF_OUT]);
 int zk_key_free(uint64_t handle);
 
+/* ---- verifier side ----------------------------------------------
+ * out = prod_i e(+-g1[i], g2[i]) with ONE final exponentiation.  Replaces Pairing.pairing and the
+ * GT sums / differences of groth16.ml:103,163-173 and pinocchio.ml:254-420 (GT is written
+ * additively there, curve.ml:212-220): `e a b + e c d - e f g` is one call with n = 3 and
+ * negate = {0, 0, 1}.  negate may be NULL.  Pairs containing the identity contribute 1.
+ * Every point must be canonical, on its curve and in the prime-order subgroup (ZK_EPOINT).
+ *
+ * A GT value is ZK_GT_BYTES opaque bytes: the 12 Fp coefficients of the library's own
+ * Fp2-Fp6-Fp12 tower, 48 B big-endian each.  It is NOT blst's GT encoding and the pairing is the
+ * cube of the reduced ate pairing (see zukelang_b200/csrc/pairing.cuh); both are invisible to a
+ * caller that only compares and multiplies GT values, which is all the reference does. */
+#define ZK_GT_BYTES 576
+int zk_pairing_product(const uint8_t *g1_96, const uint8_t *g2_192, const uint8_t *negate, size_t n,
+                       uint8_t out[ZK_GT_BYTES]);
+/* GT.( + ) of curve.ml:212-220 (the product in the multiplicative notation). */
+int zk_gt_mul(const uint8_t a[ZK_GT_BYTES], const uint8_t b[ZK_GT_BYTES], uint8_t out[ZK_GT_BYTES]);
+
+/* ---- wire format reader --------------------------------------------
+ * G1/G2.of_compressed_bytes_exn (curve.ml:201,210): n compressed points (48 B / 96 B each) ->
+ * n uncompressed points.  ZK_EPOINT when a flag byte is malformed, a coordinate is >= p, x is not
+ * on the curve, or the point is outside the prime-order subgroup. */
+int zk_g1_decompress(const uint8_t *comp48, size_t n, uint8_t *out96);
+int zk_g2_decompress(const uint8_t *comp96, size_t n, uint8_t *out192);
+
 /* ---- measurement helpers --------------------------------------------------------
  * Integer-pipe microbenchmarks.  kind: 0 = mad.lo.u32 chains,
  * 1 = mad.lo.cc / madc.hi.cc carry chains, 2 = mad.wide.u32, 3 = Fp Montgomery products

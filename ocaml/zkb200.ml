@@ -24,6 +24,10 @@ external pinocchio_pk_load : int -> int -> int array -> bytes array -> int * int
 external key_free : int64 -> unit = "zkb200_key_free"
 external groth16_prove : int64 -> int64 -> bytes -> bytes -> bytes -> bytes = "zkb200_groth16_prove"
 external pinocchio_prove : int64 -> int64 -> bytes -> bytes -> bytes = "zkb200_pinocchio_prove"
+external pairing_product : bytes -> bytes -> bytes -> bytes = "zkb200_pairing_product"   (* 96n, 192n, n flags|"" -> 576 *)
+external gt_mul : bytes -> bytes -> bytes = "zkb200_gt_mul"
+external g1_decompress : bytes -> bytes = "zkb200_g1_decompress"   (* 48n -> 96n *)
+external g2_decompress : bytes -> bytes = "zkb200_g2_decompress"   (* 96n -> 192n *)
 
 open Zukelang
 
@@ -74,6 +78,22 @@ module Bls12_381 = struct
       if List.length cs > List.length xis then invalid_arg "apply_powers";
       msm (Misclib.List.take (List.length cs) xis) cs
   end
+end
+
+(* Verifier side.  A GT value of the library is 576 opaque bytes (NOT blst's GT.t): the device
+   verifier keeps its own type and never mixes with [Curve.Bls12_381.GT].  [product] is a sum of
+   pairings in the reference's additive notation, [neg] marking the subtracted ones. *)
+module Gt_b200 = struct
+  type t = bytes
+  let zero = let b = Bytes.make 576 '\000' in Bytes.set b 47 '\001'; b
+  let ( + ) = gt_mul
+  let equal = Bytes.equal
+  let product (pairs : (Bls12_381.G1.t * Bls12_381.G2.t * bool) list) : t =
+    pairing_product
+      (cat (List.map (fun (p, _, _) -> Bls12_381.G1.to_bytes p) pairs))
+      (cat (List.map (fun (_, q, _) -> Bls12_381.G2.to_bytes q) pairs))
+      (Bytes.of_seq (Seq.map (fun (_, _, n) -> if n then '\001' else '\000') (List.to_seq pairs)))
+  let pairing p q = product [ (p, q, false) ]
 end
 
 (* Device residency of a QAP.t (QAP.ml:11-16): rows in increasing Var order, coefficients lowest
@@ -133,6 +153,13 @@ module Groth16 (C : module type of Bls12_381) = struct
     { a = G1.of_bytes_exn (Bytes.sub out 0 96);
       b = G2.of_bytes_exn (Bytes.sub out 144 192);
       c = G1.of_bytes_exn (Bytes.sub out 432 96) }
+
+  (* groth16.ml:163-173 with the right-hand pairings moved to the left: one product, one final
+     exponentiation.  [ab] must be [Gt_b200.pairing pk.a pk.b2] (the reference's vkey.ab is a blst
+     GT.t and cannot be compared with a device GT value). *)
+  let verify_b200 ~(ab : Gt_b200.t) w_io (vk : vkey) (pr : proof) =
+    Gt_b200.equal ab
+      (Gt_b200.product [ (pr.a, pr.b, false); (G1.dot vk.ltgm_io w_io, vk.gm, true); (pr.c, vk.d, true) ])
 end
 
 (* Pinocchio.Make (C).{NonZK, ZK}.prove, pinocchio.ml:536-538 / 559-561. *)

@@ -237,3 +237,76 @@ CAMLprim value zkb200_g2_sum(value pts) {
   memcpy(Bytes_val(out), res, ZK_G2_OUT);
   CAMLreturn(out);
 }
+
+/* ---- verifier side -------------------------------------------------------------------------- */
+/* pairing_product : bytes (n G1, uncompressed) -> bytes (n G2) -> bytes (n negate flags, or empty)
+ *                   -> bytes (ZK_GT_BYTES).  Replaces Pairing.pairing and the GT sums of
+ *                   groth16.ml:163-173 / pinocchio.ml:254-420. */
+CAMLprim value zkb200_pairing_product(value g1, value g2, value neg) {
+  CAMLparam3(g1, g2, neg);
+  CAMLlocal1(out);
+  size_t n1, n2, nn;
+  uint8_t *a = dup_bytes(g1, &n1);
+  uint8_t *b = dup_bytes(g2, &n2);
+  uint8_t *f = dup_bytes(neg, &nn);
+  size_t n = n1 / ZK_G1_RAW;
+  uint8_t res[ZK_GT_BYTES];
+  int rc = ZK_EARG;
+  if (n1 % ZK_G1_RAW == 0 && n2 == n * ZK_G2_RAW && (nn == 0 || nn == n)) {
+    caml_release_runtime_system();
+    rc = zk_pairing_product(a, b, nn ? f : NULL, n, res);
+    caml_acquire_runtime_system();
+  }
+  free(a); free(b); free(f);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(ZK_GT_BYTES);
+  memcpy(Bytes_val(out), res, ZK_GT_BYTES);
+  CAMLreturn(out);
+}
+
+/* gt_mul : bytes -> bytes -> bytes   (GT.( + ) of curve.ml:212-220) */
+CAMLprim value zkb200_gt_mul(value x, value y) {
+  CAMLparam2(x, y);
+  CAMLlocal1(out);
+  size_t nx, ny;
+  uint8_t *a = dup_bytes(x, &nx);
+  uint8_t *b = dup_bytes(y, &ny);
+  uint8_t res[ZK_GT_BYTES];
+  int rc = ZK_EARG;
+  if (nx == ZK_GT_BYTES && ny == ZK_GT_BYTES) {
+    caml_release_runtime_system();
+    rc = zk_gt_mul(a, b, res);
+    caml_acquire_runtime_system();
+  }
+  free(a); free(b);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(ZK_GT_BYTES);
+  memcpy(Bytes_val(out), res, ZK_GT_BYTES);
+  CAMLreturn(out);
+}
+
+/* g1_decompress / g2_decompress : bytes (n compressed points) -> bytes (n uncompressed points)
+ * (G1/G2.of_compressed_bytes_exn, curve.ml:201,210, over a batch) */
+static value decompress_stub(value comp, int g2) {
+  CAMLparam1(comp);
+  CAMLlocal1(out);
+  const size_t cb = g2 ? ZK_G2_COMP : ZK_G1_COMP, rb = g2 ? ZK_G2_RAW : ZK_G1_RAW;
+  size_t nb;
+  uint8_t *in = dup_bytes(comp, &nb);
+  size_t n = nb / cb;
+  uint8_t *res = (uint8_t *)malloc(n * rb + 1);
+  int rc = ZK_EARG;
+  if (res && nb % cb == 0 && n > 0) {
+    caml_release_runtime_system();
+    rc = g2 ? zk_g2_decompress(in, n, res) : zk_g1_decompress(in, n, res);
+    caml_acquire_runtime_system();
+  }
+  free(in);
+  if (rc) { free(res); zk_raise(rc); }
+  out = caml_alloc_string(n * rb);
+  memcpy(Bytes_val(out), res, n * rb);
+  free(res);
+  CAMLreturn(out);
+}
+CAMLprim value zkb200_g1_decompress(value comp) { return decompress_stub(comp, 0); }
+CAMLprim value zkb200_g2_decompress(value comp) { return decompress_stub(comp, 1); }

@@ -104,3 +104,31 @@ def decode_pinocchio_proof(proof):
     from zukelang_b200.pinocchio import PROOF_FIELDS, PROOF_IS_G2
     return {f: (O.g2_from_uncompressed if g2 else O.g1_from_uncompressed)(getattr(proof, f).raw)
             for f, g2 in zip(PROOF_FIELDS, PROOF_IS_G2)}
+
+
+# ---- GT: C-ABI bytes (tower coefficients) <-> oracle/pairing.py tuples ---------------------------
+def gt_bytes_to_oracle(b):
+    """576 B of include/zkb200.h (slot a_j of c_i = the Fp2 coefficient x + y u of w^(2j+i), stored
+    x then y, 48 B big-endian) -> the oracle's coefficients of w^0..w^11 with u = w^6 - 1."""
+    assert len(b) == 576
+    c = [int.from_bytes(b[48 * k:48 * k + 48], "big") for k in range(12)]
+    t = [0] * 12
+    o = 0
+    for i in range(2):
+        for j in range(3):
+            k = 2 * j + i
+            x, y = c[o], c[o + 1]
+            o += 2
+            t[k] = (x - y) % P
+            t[k + 6] = y
+    return tuple(t)
+
+
+def oracle_to_gt_bytes(t):
+    out = b""
+    for i in range(2):
+        for j in range(3):
+            k = 2 * j + i
+            y = t[k + 6]
+            out += ((t[k] + y) % P).to_bytes(48, "big") + y.to_bytes(48, "big")
+    return out

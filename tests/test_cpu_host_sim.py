@@ -127,3 +127,120 @@ def test_xyzz_formulas(sim, G):
         assert _ec(sim, G, 2, _enc_xyzz(G, p, z, w), []) == G.add(p, p)
     for k in (0, 1, R - 1, rng.randrange(R)):
         assert _ec(sim, G, 3, _enc_xyzz(G, pts[1], 12345, w), [], k) == G.mul(pts[1], k)
+
+
+# ---- Fp12 tower / pairing / square roots (pairing.cuh) ------------------------------------------
+@pytest.fixture(scope="module")
+def simp():
+    out = tempfile.mkdtemp(prefix="zk_host_sim_")
+    so = os.path.join(out, "sim_pairing.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DZK_HOST_SIM", "-shared", "-fPIC", "-x", "c++",
+                           os.path.join(SIM, "sim_pairing.cpp"), "-o", so])
+    return ctypes.CDLL(so)
+
+
+def _tower_to_limbs(t):
+    """oracle Fp12 (coefficients of w^0..w^11, w^12 = 2 w^6 - 2) -> device tower limbs.
+    Slot a_j of c_i is the Fp2 coefficient x + y u of w^(2j+i); u = w^6 - 1."""
+    out = []
+    for i in range(2):
+        for j in range(3):
+            k = 2 * j + i
+            y = t[k + 6]
+            x = (t[k] + y) % P
+            out += _fpl(x) + _fpl(y)
+    return out
+
+
+def _limbs_to_tower(l):
+    t = [0] * 12
+    o = 0
+    for i in range(2):
+        for j in range(3):
+            k = 2 * j + i
+            x, y = _unfp(l[o:o + 12]), _unfp(l[o + 12:o + 24])
+            o += 24
+            t[k] = (x - y) % P
+            t[k + 6] = y
+    return tuple(t)
+
+
+def _f12(simp, op, a, b=None):
+    A = (ctypes.c_uint32 * 144)(*_tower_to_limbs(a))
+    B = (ctypes.c_uint32 * 144)(*_tower_to_limbs(b if b is not None else a))
+    Out = (ctypes.c_uint32 * 144)()
+    simp.sim_f12_op(op, A, B, Out)
+    return _limbs_to_tower(list(Out))
+
+
+def test_fp12_tower_matches_the_oracle_field(simp):
+    from oracle import pairing as OP
+    rng = random.Random(21)
+    a = tuple(rng.randrange(P) for _ in range(12))
+    b = tuple(rng.randrange(P) for _ in range(12))
+    assert _f12(simp, 0, a, b) == OP.f12_mul(a, b)
+    assert _f12(simp, 1, a) == OP.f12_mul(a, a)
+    assert OP.f12_mul(_f12(simp, 2, a), a) == OP.F12_ONE
+    assert _f12(simp, 3, a) == OP.f12_pow(a, P)                       # Frobenius
+    assert _f12(simp, 4, a) == OP.f12_pow(a, P ** 6)                  # conjugation
+    u = OP.f12_pow(a, (P ** 6 - 1) * (P ** 2 + 1))                    # a unitary element
+    assert OP.f12_mul(_f12(simp, 5, u), OP.f12_pow(u, OP.ATE_LOOP)) == OP.F12_ONE   # u^z, z < 0
+
+
+def test_miller_loop_and_final_exponentiation_match_the_oracle(simp):
+    from oracle import pairing as OP
+    rng = random.Random(22)
+    p = G1.mul(G1.one, rng.randrange(1, R))
+    q = G2.mul(G2.one, rng.randrange(1, R))
+    Pl = (ctypes.c_uint32 * 24)(*_enc_aff(G1, p, 12))
+    Ql = (ctypes.c_uint32 * 48)(*_enc_aff(G2, q, 24))
+    F = (ctypes.c_uint32 * 144)()
+    simp.sim_miller(Pl, Ql, F)
+    f = _limbs_to_tower(list(F))
+    assert f == OP.miller_loop(p, q)                                  # same lines, same loop
+    E = (ctypes.c_uint32 * 144)()
+    simp.sim_final_exp(F, E)
+    e = _limbs_to_tower(list(E))
+    assert e == OP.f12_pow(OP.pairing(p, q), 3)                       # hard part carries the factor 3
+    assert e != OP.F12_ONE and OP.f12_pow(e, R) == OP.F12_ONE
+
+
+def test_square_roots_and_subgroup_check(simp):
+    rng = random.Random(23)
+    for _ in range(6):
+        a = rng.randrange(P)
+        sq = a * a % P
+        Out = (ctypes.c_uint32 * 12)()
+        assert simp.sim_fp_sqrt((ctypes.c_uint32 * 12)(*_fpl(sq)), Out) == 1
+        assert _unfp(list(Out)) in (a, P - a)
+        nonsq = sq * (P - 1) % P                                      # -1 is a non-residue (p = 3 mod 4)
+        assert simp.sim_fp_sqrt((ctypes.c_uint32 * 12)(*_fpl(nonsq)), Out) == (1 if sq == 0 else 0)
+    F2 = G2.F
+    n_roots = n_none = 0
+    cases = [(rng.randrange(P), rng.randrange(P)) for _ in range(8)]
+    cases += [(rng.randrange(P), 0), (0, rng.randrange(P)), (0, 0), (P - 4, 0), (P - 1, 0)]
+    for c in cases:
+        for a in (F2.mul(c, c), c):
+            Out = (ctypes.c_uint32 * 24)()
+            ok = simp.sim_fp2_sqrt((ctypes.c_uint32 * 24)(*(_fpl(a[0]) + _fpl(a[1]))), Out)
+            if ok:
+                y = (_unfp(list(Out)[:12]), _unfp(list(Out)[12:]))
+                assert F2.mul(y, y) == (a[0] % P, a[1] % P)
+                n_roots += 1
+            else:
+                # a has no square root: its norm is a non-residue in Fp
+                nrm = (a[0] * a[0] + a[1] * a[1]) % P
+                assert pow(nrm, (P - 1) // 2, P) == P - 1
+                n_none += 1
+    assert n_roots >= len(cases) and n_none >= 1
+    # subgroup membership: generator multiples pass, a curve point outside the subgroup fails
+    assert simp.sim_in_subgroup(0, (ctypes.c_uint32 * 24)(*_enc_aff(G1, G1.mul(G1.one, 77), 12))) == 1
+    assert simp.sim_in_subgroup(1, (ctypes.c_uint32 * 48)(*_enc_aff(G2, G2.mul(G2.one, 77), 24))) == 1
+    x = 1
+    while True:                                                       # first x with x^3 + 4 a square
+        y2 = (x ** 3 + 4) % P
+        y = pow(y2, (P + 1) // 4, P)
+        if y * y % P == y2 and G1.add(G1.mul((x, y), R - 1), (x, y)) is not None:   # [r]P != O
+            break
+        x += 1
+    assert simp.sim_in_subgroup(0, (ctypes.c_uint32 * 24)(*_enc_aff(G1, (x, y), 12))) == 0

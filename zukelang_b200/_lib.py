@@ -15,6 +15,7 @@ ZK_OK, ZK_EARG, ZK_EPOINT, ZK_ECUDA, ZK_EREMAINDER = 0, -1, -2, -3, -4
 FR_BYTES, G1_RAW, G1_COMP, G1_OUT, G2_RAW, G2_COMP, G2_OUT = 32, 96, 48, 144, 192, 96, 288
 GROTH16_PROOF_OUT = G1_OUT + G2_OUT + G1_OUT
 PINOCCHIO_PROOF_OUT = 6 * G1_OUT + 2 * G2_OUT
+GT_BYTES = 576
 
 
 class ZkError(RuntimeError):
@@ -73,6 +74,10 @@ SIGNATURES = {
     "zk_pinocchio_pk_load": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64)]),
     "zk_pinocchio_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),
     "zk_key_free": (c_int, [c_uint64]),
+    "zk_pairing_product": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "zk_gt_mul": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "zk_g1_decompress": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "zk_g2_decompress": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_bench_intpipe": (c_int, [c_int, c_int, POINTER(c_double), POINTER(c_double)]),
     "zk_test_field_op": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
 }

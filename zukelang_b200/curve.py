@@ -4,7 +4,9 @@
 host).  ``G1`` / ``G2`` values are opaque byte-backed points (the counterpart of the
 reference's custom blocks) and EVERY group operation — ``+``, ``*``, ``~-``, ``sum``,
 ``dot``, ``apply_powers``, ``powers``, ``of_Fr`` — is executed by the CUDA library
-through the C ABI (``zk_g*_msm`` / ``zk_g*_fixed_base_mul``).  ``README.md:36-40`` of
+through the C ABI (``zk_g*_msm`` / ``zk_g*_fixed_base_mul``).  ``GT`` / ``Pairing`` (the verifier
+side, curve.ml:212-220) go through ``zk_pairing_product`` / ``zk_gt_mul`` and
+``of_compressed_bytes_exn`` through ``zk_g*_decompress``.  ``README.md:36-40`` of
 the reference spells the module ``Ecp``; ``Ecp = Curve`` aliases are provided in
 ``zukelang_b200/__init__``-level imports for both spellings.
 """
@@ -20,6 +22,7 @@ from . import _lib
 Var = Tuple[str, int]
 
 R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+_P_HALF = (0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB - 1) // 2
 
 
 class Fr:
@@ -176,13 +179,37 @@ class _Group:
         return self.msm(list(xis[:len(cs)]), list(cs))
 
     def to_compressed_bytes(self, a: Point) -> bytes:
-        """curve.ml:199 / :208."""
+        """curve.ml:199 / :208.  Results of device calls already carry the compressed form; for
+        the others it is a re-flagging of the uncompressed bytes (x with the three flag bits, the
+        sign bit by comparing the canonical y with (p-1)/2 — c1 first, then c0, in G2): a byte
+        format conversion, no field arithmetic."""
         if a._comp is None:
-            a._comp = self.msm([a], [1])._comp
+            half = self.RAW // 2
+            if a.raw[0] & 0x40:
+                a._comp = bytes([0xC0]) + bytes(half - 1)
+            else:
+                y = [int.from_bytes(a.raw[half + o:half + o + 48], "big") for o in range(0, half, 48)]
+                lead = next((c for c in y if c), 0)                       # G2 wire order is c1 | c0
+                a._comp = bytes([a.raw[0] | 0x80 | (0x20 if lead > _P_HALF else 0)]) + a.raw[1:half]
         return a._comp
 
     def to_bytes(self, a: Point) -> bytes:
         return a.raw
+
+    def of_compressed_bytes_many(self, blobs: Sequence[bytes]) -> List[Point]:
+        """``of_compressed_bytes_exn`` (curve.ml:201 / :210) over a batch: one device call."""
+        n = len(blobs)
+        if n == 0:
+            return []
+        if any(len(b) != self.COMP for b in blobs):
+            raise _lib.InvalidArgument(_lib.ZK_EARG, "of_compressed_bytes_exn: wrong length")
+        out = (ctypes.c_uint8 * (self.RAW * n))()
+        _lib.check(getattr(_lib.lib(), "zk_%s_decompress" % self.name.lower())(b"".join(blobs), n, out))
+        raw = bytes(out)
+        return [Point(raw[i * self.RAW:(i + 1) * self.RAW], bytes(blobs[i])) for i in range(n)]
+
+    def of_compressed_bytes_exn(self, b: bytes) -> Point:
+        return self.of_compressed_bytes_many([b])[0]
 
 
 _G1_GEN = ("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
@@ -193,9 +220,75 @@ _G2_GEN = ("13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334c
            "0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801")
 
 
+class GTElem:
+    """An opaque GT element (576 bytes in the library's own encoding, include/zkb200.h)."""
+    __slots__ = ("raw",)
+
+    def __init__(self, raw: bytes):
+        if len(raw) != _lib.GT_BYTES:
+            raise _lib.InvalidArgument(_lib.ZK_EARG, "GT.of_bytes_exn: wrong length")
+        self.raw = bytes(raw)
+
+    def __eq__(self, other):
+        return isinstance(other, GTElem) and self.raw == other.raw
+
+    def __hash__(self):
+        return hash(self.raw)
+
+    def __repr__(self):
+        return "GT(%s…)" % self.raw[40:48].hex()
+
+
+class _GT:
+    """``GT`` with ExtendG's additive notation (curve.ml:212-220): ``+`` is the GT product."""
+    zero = GTElem((1).to_bytes(48, "big") + bytes(_lib.GT_BYTES - 48))     # the neutral element
+
+    @staticmethod
+    def add(a: GTElem, b: GTElem) -> GTElem:
+        out = (ctypes.c_uint8 * _lib.GT_BYTES)()
+        _lib.check(_lib.lib().zk_gt_mul(a.raw, b.raw, out))
+        return GTElem(bytes(out))
+
+    @staticmethod
+    def eq(a: GTElem, b: GTElem) -> bool:
+        return a.raw == b.raw
+
+    @staticmethod
+    def to_bytes(a: GTElem) -> bytes:
+        return a.raw
+
+    @staticmethod
+    def of_bytes_exn(b: bytes) -> GTElem:
+        return GTElem(b)
+
+
+class _Pairing:
+    """``Bls12_381.Pairing`` as used at groth16.ml:103,168 and pinocchio.ml:269."""
+
+    @staticmethod
+    def product(pairs: Sequence[Tuple[Point, Point]], negate: Sequence[bool] | None = None) -> GTElem:
+        """prod_i e(+-p_i, q_i) with one final exponentiation: a GT sum / difference of pairings
+        (``e a b + e c d - e f g`` in the reference's additive notation) as ONE device call."""
+        n = len(pairs)
+        if n == 0:
+            return _GT.zero
+        neg = bytes(1 if x else 0 for x in negate) if negate is not None else None
+        if neg is not None and len(neg) != n:
+            raise _lib.InvalidArgument(_lib.ZK_EARG, "pairing: length mismatch")
+        out = (ctypes.c_uint8 * _lib.GT_BYTES)()
+        _lib.check(_lib.lib().zk_pairing_product(b"".join(p.raw for p, _ in pairs), b"".join(q.raw for _, q in pairs),
+                                                 neg, n, out))
+        return GTElem(bytes(out))
+
+    @staticmethod
+    def pairing(p: Point, q: Point) -> GTElem:
+        return _Pairing.product([(p, q)])
+
+
 class Bls12_381:
-    """``Curve.Bls12_381`` (curve.mli:56-60).  GT / Pairing belong to the verifier and are
-    outside the accelerated path."""
+    """``Curve.Bls12_381`` (curve.mli:46-60): Fr, G1, G2, GT and Pairing."""
     Fr = Fr
     G1 = _Group("G1", 96, 48, _G1_GEN)
     G2 = _Group("G2", 192, 96, _G2_GEN)
+    GT = _GT
+    Pairing = _Pairing

@@ -36,7 +36,7 @@ class PKey:
 
 @dataclass
 class VKey:
-    """groth16.ml:36-43 (``ab`` is a GT element: produced by the verifier side, not here)."""
+    """groth16.ml:36-43."""
     one1: Point
     ltgm_io: Dict[Var, Point]
     one2: Point
@@ -98,7 +98,8 @@ class Make(ProtocolS):
         ltgm = p1[o:]
         pkey = PKey(a=p1[0], d1=p1[1], ti1=ti1, ltd_mid=dict(zip(mids, ltd)), tiztd=tiztd, b1=p1[2],
                     b2=p2[0], d2=p2[1], ti2=p2[3:])
-        vkey = VKey(one1=G1.one, ltgm_io=dict(zip(ios, ltgm)), one2=G2.one, gm=p2[2], d=p2[1])
+        vkey = VKey(one1=G1.one, ltgm_io=dict(zip(ios, ltgm)), one2=G2.one, gm=p2[2], d=p2[1],
+                    ab=self.C.Pairing.pairing(p1[0], p2[0]))               # :103
         return pkey, vkey
 
     # ---- device key --------------------------------------------------------------------
@@ -148,6 +149,16 @@ class Make(ProtocolS):
         bb = Point(b[144:336], b[336:432])
         c = Point(b[432:528], b[528:576])
         return Proof(a, bb, c)
+
+    # ---- groth16.ml:163-173 ---------------------------------------------------------------
+    def verify(self, w_io: Dict[Var, int], vkey: VKey, proof: Proof) -> bool:
+        """``e a b = ab + e (dot ltgm_io w_io) gm + e c d`` in GT.  The two pairings of the right-hand
+        side move to the left (negated) so that the whole check is one pairing product — one final
+        exponentiation — compared with the stored ``ab``."""
+        G1, Pairing = self.C.G1, self.C.Pairing
+        io = G1.dot(vkey.ltgm_io, w_io)                                  # Domain mismatch -> assert
+        lhs = Pairing.product([(proof.a, proof.b), (io, vkey.gm), (proof.c, vkey.d)], [False, True, True])
+        return self.C.GT.eq(lhs, vkey.ab)
 
     @staticmethod
     def free(pkey: PKey) -> None:
