@@ -217,7 +217,7 @@ int zk_key_free(uint64_t handle);
  * out = prod_i e(+-g1[i], g2[i]) with ONE final exponentiation.  Replaces Pairing.pairing and the
  * GT sums / differences of groth16.ml:103,163-173 and pinocchio.ml:254-420 (GT is written
  * additively there, curve.ml:212-220): `e a b + e c d - e f g` is one call with n = 3 and
- * negate = {0, 0, 1}.  negate may be NULL.  Pairs containing the identity contribute 1.
+ * negate = {0, 0, 1}.  negate may be NULL.  Pairs containing the identity contribute 1.  n <= 4096.
  * Every point must be canonical, on its curve and in the prime-order subgroup (ZK_EPOINT).
  *
  * A GT value is ZK_GT_BYTES opaque bytes: the 12 Fp coefficients of the library's own
@@ -227,6 +227,11 @@ int zk_key_free(uint64_t handle);
 #define ZK_GT_BYTES 576
 int zk_pairing_product(const uint8_t *g1_96, const uint8_t *g2_192, const uint8_t *negate, size_t n,
                        uint8_t out[ZK_GT_BYTES]);
+/* k independent products in one call: product g takes the next counts[g] pairs of g1 / g2 / negate
+ * (sum of counts <= 4096) and writes out[g * ZK_GT_BYTES ..].  A verifier with several GT
+ * equations (the five checks of pinocchio.ml:254-420) pays the latency of one. */
+int zk_pairing_product_batch(const uint8_t *g1_96, const uint8_t *g2_192, const uint8_t *negate,
+                             const uint32_t *counts, size_t k, uint8_t *out);
 /* GT.( + ) of curve.ml:212-220 (the product in the multiplicative notation). */
 int zk_gt_mul(const uint8_t a[ZK_GT_BYTES], const uint8_t b[ZK_GT_BYTES], uint8_t out[ZK_GT_BYTES]);
 

@@ -188,6 +188,44 @@ def test_pinocchio_verify_on_the_device(zk):
     q.free()
 
 
+@pytest.mark.parametrize("which", ["groth16", "pinocchio_nonzk", "pinocchio_zk"])
+def test_protocol_harness_round_trip(zk, which):
+    """``Test.Make(F)(Protocol)`` behind the front-end (test.ml:119-178): keygen, prove, verify on the
+    public part of the witness — the reference's own acceptance test, no oracle in the loop."""
+    from zukelang_b200 import groth16 as G16, pinocchio as PN
+    from zukelang_b200.protocol import Test
+    proto = {"groth16": G16.Make(), "pinocchio_nonzk": PN.Make().NonZK, "pinocchio_zk": PN.Make().ZK}[which]
+    rng = random.Random(81)
+    for (circ, wit), x in ((Z.circuit_cubic(), 10), (Z.circuit_pair_case(5), 6), (Z.circuit_mulchain(20), 3)):
+        oq = Z.qap_build(circ.gates)
+        q = H.mirror_qap(oq)
+        Test(proto).run(rng, H.mirror_circuit(circ), q, wit(x))
+        q.free()
+    # a witness that violates a gate never reaches the verifier: QAP.eval asserts (QAP.ml:134)
+    circ, wit = Z.circuit_cubic()
+    q = H.mirror_qap(Z.qap_build(circ.gates))
+    sol = wit(10)
+    k = sorted(set(circ.mids))[0]
+    with pytest.raises(AssertionError):
+        Test(proto).run(rng, H.mirror_circuit(circ), q, {**sol, k: (sol[k] + 1) % R})
+    q.free()
+
+
+def test_batched_pairing_products(zk):
+    from zukelang_b200.curve import Bls12_381 as C
+    g1 = C.G1.fixed_base([3, 5, 15, 7])
+    g2 = C.G2.fixed_base([5, 3, 1, 11])
+    e = C.Pairing.product
+    groups = [([(g1[0], g2[0]), (g1[2], g2[2])], [False, True]),        # e(3G,5H) / e(15G,H) = 1
+              ([], None),
+              ([(g1[3], g2[3])], None),
+              ([(g1[0], g2[0]), (g1[1], g2[1])], [False, True])]         # e(3G,5H) / e(5G,3H) = 1
+    got = C.Pairing.products(groups)
+    assert got[0] == C.GT.zero and got[1] == C.GT.zero and got[3] == C.GT.zero
+    assert got[2] == e([(g1[3], g2[3])]) and got[2] != C.GT.zero
+    assert [x for x in got] == [e(p, n) for p, n in groups]
+
+
 def test_wire_formats_round_trip(zk):
     from zukelang_b200 import groth16 as G16, pinocchio as PN, wire
     circ, wit = Z.circuit_cubic()

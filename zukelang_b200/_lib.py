@@ -75,6 +75,7 @@ SIGNATURES = {
     "zk_pinocchio_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]),
     "zk_key_free": (c_int, [c_uint64]),
     "zk_pairing_product": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "zk_pairing_product_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "zk_gt_mul": (c_int, [c_void_p, c_void_p, c_void_p]),
     "zk_g1_decompress": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_g2_decompress": (c_int, [c_void_p, c_size_t, c_void_p]),

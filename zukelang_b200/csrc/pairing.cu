@@ -50,12 +50,19 @@ k_pairing_miller(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2,
   out[i] = miller_loop(p, q);
 }
 
+// blockIdx.x = product g: multiplies the Miller values of pairs [first[g], first[g+1]) and runs the
+// final exponentiation of that product (an empty range gives 1)
 static __global__ void __launch_bounds__(32)
-k_pairing_final(const Fp12* __restrict__ f, uint32_t n, uint8_t* __restrict__ out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Fp12 acc = f[0];
-  for (uint32_t i = 1; i < n; i++) acc = f12_mul(acc, f[i]);
-  gt_serialize(final_exponentiation(acc), out);
+k_pairing_final(const Fp12* __restrict__ f, const uint32_t* __restrict__ first, uint8_t* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  const uint32_t g = blockIdx.x, lo = first[g], hi = first[g + 1];
+  Fp12 acc = Fp12::one();
+  if (lo < hi) {
+    acc = f[lo];
+    for (uint32_t i = lo + 1; i < hi; i++) acc = f12_mul(acc, f[i]);
+    acc = final_exponentiation(acc);
+  }
+  gt_serialize(acc, out + (size_t)g * ZK_GT_BYTES);
 }
 
 static __global__ void __launch_bounds__(32)
@@ -146,28 +153,47 @@ using namespace zk;
 
 extern "C" {
 
-int zk_pairing_product(const uint8_t* g1, const uint8_t* g2, const uint8_t* negate, size_t n, uint8_t* out) {
+// k products over consecutive runs of pairs: counts[g] pairs feed product g
+static int pairing_products(const uint8_t* g1, const uint8_t* g2, const uint8_t* negate, const uint32_t* counts,
+                            size_t k, uint8_t* out) {
   ZK_API_BEGIN
-  ZK_REQUIRE(g1 && g2 && out && n > 0 && n <= 1024, ZK_EARG, "pairing_product: bad arguments");
+  ZK_REQUIRE(g1 && g2 && out && counts && k > 0 && k <= 1024, ZK_EARG, "pairing_product: bad arguments");
+  std::vector<uint32_t> first(k + 1, 0);
+  for (size_t g = 0; g < k; g++) first[g + 1] = first[g] + counts[g];
+  const size_t n = first[k];
+  ZK_REQUIRE(n > 0 && n <= 4096, ZK_EARG, "pairing_product: bad pair count");
   cudaStream_t st = default_stream();
-  DevBuf<uint8_t> d_g1(n * G1Traits::RAW), d_g2(n * G2Traits::RAW), d_neg(n), d_out(ZK_GT_BYTES);
+  DevBuf<uint8_t> d_g1(n * G1Traits::RAW), d_g2(n * G2Traits::RAW), d_neg(n), d_out(k * ZK_GT_BYTES);
   DevBuf<Fp12> d_f(n);
+  DevBuf<uint32_t> d_first(k + 1);
   DevBuf<int> d_err(1);
   ZK_CUDA(cudaMemcpyAsync(d_g1.p, g1, n * G1Traits::RAW, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(d_g2.p, g2, n * G2Traits::RAW, cudaMemcpyHostToDevice, st));
   if (negate) ZK_CUDA(cudaMemcpyAsync(d_neg.p, negate, n, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(d_first.p, first.data(), (k + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
   k_pairing_miller<<<dim3((unsigned)n, 3), 32, 0, st>>>(d_g1.p, d_g2.p, negate ? d_neg.p : nullptr, (uint32_t)n, d_f.p, d_err.p);
   ZK_CUDA(cudaGetLastError());
-  k_pairing_final<<<1, 32, 0, st>>>(d_f.p, (uint32_t)n, d_out.p);
+  k_pairing_final<<<(unsigned)k, 32, 0, st>>>(d_f.p, d_first.p, d_out.p);
   ZK_CUDA(cudaGetLastError());
   int err = 0;
   ZK_CUDA(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaMemcpyAsync(out, d_out.p, ZK_GT_BYTES, cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_CUDA(cudaMemcpyAsync(out, d_out.p, k * ZK_GT_BYTES, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));   // first[] and the outputs are done with
   ZK_REQUIRE(err != 1, ZK_EPOINT, "pairing_product: point not canonical or not on the curve");
   ZK_REQUIRE(err != 2, ZK_EPOINT, "pairing_product: point is not in the prime-order subgroup");
   ZK_API_END
+}
+
+int zk_pairing_product(const uint8_t* g1, const uint8_t* g2, const uint8_t* negate, size_t n, uint8_t* out) {
+  const uint32_t count = (uint32_t)n;
+  if (n == 0 || n > 4096) { zk::set_error("pairing_product: bad arguments"); return ZK_EARG; }
+  return pairing_products(g1, g2, negate, &count, 1, out);
+}
+
+int zk_pairing_product_batch(const uint8_t* g1, const uint8_t* g2, const uint8_t* negate, const uint32_t* counts,
+                             size_t k, uint8_t* out) {
+  return pairing_products(g1, g2, negate, counts, k, out);
 }
 
 int zk_gt_mul(const uint8_t* a, const uint8_t* b, uint8_t* out) {

@@ -281,6 +281,29 @@ class _Pairing:
         return GTElem(bytes(out))
 
     @staticmethod
+    def products(groups: Sequence[Tuple[Sequence[Tuple[Point, Point]], Sequence[bool] | None]]) -> List[GTElem]:
+        """Several independent pairing products in ONE device call (their Miller loops and final
+        exponentiations run side by side): ``groups`` is a list of ``(pairs, negate)``."""
+        k = len(groups)
+        if k == 0:
+            return []
+        g1, g2, neg, counts = [], [], bytearray(), []
+        for pairs, negate in groups:
+            if negate is not None and len(negate) != len(pairs):
+                raise _lib.InvalidArgument(_lib.ZK_EARG, "pairing: length mismatch")
+            counts.append(len(pairs))
+            g1 += [p.raw for p, _ in pairs]
+            g2 += [q.raw for _, q in pairs]
+            neg += bytes(1 if x else 0 for x in (negate if negate is not None else [False] * len(pairs)))
+        if not g1:
+            return [_GT.zero] * k
+        out = (ctypes.c_uint8 * (_lib.GT_BYTES * k))()
+        _lib.check(_lib.lib().zk_pairing_product_batch(b"".join(g1), b"".join(g2), bytes(neg),
+                                                       (ctypes.c_uint32 * k)(*counts), k, out))
+        b = bytes(out)
+        return [GTElem(b[i * _lib.GT_BYTES:(i + 1) * _lib.GT_BYTES]) for i in range(k)]
+
+    @staticmethod
     def pairing(p: Point, q: Point) -> GTElem:
         return _Pairing.product([(p, q)])
 

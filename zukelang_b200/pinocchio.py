@@ -175,22 +175,24 @@ class _Base(ProtocolS):
         """The four knowledge-of-coefficient checks are ``assert``s in the reference (:296, :311,
         :326, :380): they raise here too; the divisibility check (:416-419) is the boolean result.
         Every GT equation ``lhs = rhs`` is evaluated as one pairing product ``lhs - rhs = 0``."""
-        G1, G2, GT, e = self.C.G1, self.C.G2, self.C.GT, self.C.Pairing.product
-        is_zero = lambda pairs, neg: GT.eq(e(pairs, neg), GT.zero)
-        if not is_zero([(proof.vv, vkey["av"]), (proof.vavv, vkey["one2"])], [False, True]):
-            raise AssertionError("Pinocchio.verify: KC check of vv failed")
-        if not is_zero([(vkey["aw"], proof.ww), (vkey["one"], proof.waww)], [False, True]):
-            raise AssertionError("Pinocchio.verify: KC check of ww failed")
-        if not is_zero([(proof.yy, vkey["ay"]), (proof.yayy, vkey["one2"])], [False, True]):
-            raise AssertionError("Pinocchio.verify: KC check of yy failed")
-        if not is_zero([(proof.bvwy, vkey["gm2"]), (proof.vv, vkey["bgm2"]), (vkey["bgm"], proof.ww),
-                        (proof.yy, vkey["bgm2"])], [False, True, True, True]):
-            raise AssertionError("Pinocchio.verify: same-coefficient check failed")
+        G1, G2, GT = self.C.G1, self.C.G2, self.C.GT
         vio = G1.dot(vkey["vv_io"], ios)                                  # Domain mismatch -> assert (:383,:392,:401)
         wio = G2.dot(vkey["ww_io"], ios)
         yio = G1.dot(vkey["yy_io"], ios)
-        return is_zero([(G1.add(vio, proof.vv), G2.add(wio, proof.ww)), (G1.add(yio, proof.yy), vkey["one2"]),
-                        (proof.h, vkey["yt"])], [False, True, True])
+        # all five equations in one device call: Miller loops and final exponentiations side by side
+        checks = self.C.Pairing.products([
+            ([(proof.vv, vkey["av"]), (proof.vavv, vkey["one2"])], [False, True]),                       # :296
+            ([(vkey["aw"], proof.ww), (vkey["one"], proof.waww)], [False, True]),                        # :311
+            ([(proof.yy, vkey["ay"]), (proof.yayy, vkey["one2"])], [False, True]),                       # :326
+            ([(proof.bvwy, vkey["gm2"]), (proof.vv, vkey["bgm2"]), (vkey["bgm"], proof.ww),
+              (proof.yy, vkey["bgm2"])], [False, True, True, True]),                                     # :380
+            ([(G1.add(vio, proof.vv), G2.add(wio, proof.ww)), (G1.add(yio, proof.yy), vkey["one2"]),
+              (proof.h, vkey["yt"])], [False, True, True]),                                              # :416-419
+        ])
+        for ok, what in zip(checks[:4], ("KC check of vv", "KC check of ww", "KC check of yy", "same-coefficient check")):
+            if not GT.eq(ok, GT.zero):
+                raise AssertionError("Pinocchio.verify: %s failed" % what)
+        return GT.eq(checks[4], GT.zero)
 
     @staticmethod
     def free(pkey: PKey) -> None:

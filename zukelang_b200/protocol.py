@@ -36,3 +36,26 @@ class ProtocolS:
 
     def verify(self, input_output: Dict[Var, int], vkey, proof) -> bool:
         raise NotImplementedError                                      # pragma: no cover
+
+
+class Test:
+    """``Test.Make(F)(Protocol)`` (src/lib/test/test.mli:4-25), the part behind the DSL front-end:
+    what ``test`` / ``random_test`` do once ``Comp.compile``, ``QAP.build`` and the witness
+    evaluation have produced ``circuit``, ``qap`` and ``sol`` (test.ml:60-97, 119-178) —
+    ``keygen``, ``prove``, ``public = sol`` minus the circuit's mids, ``assert (verify …)``."""
+
+    def __init__(self, protocol: ProtocolS):
+        self.protocol = protocol
+
+    def run(self, rng: random.Random, circuit: Circuit, qap, sol: Dict[Var, int]):
+        pkey, vkey = self.protocol.keygen(rng, circuit, qap)             # test.ml:121-122
+        try:
+            proof = self.protocol.prove(rng, qap, pkey, sol)             # :170
+            mids = set(circuit.mids)
+            public = {k: v for k, v in sol.items() if k not in mids}     # :174-176
+            assert self.protocol.verify(public, vkey, proof), "Protocol.verify rejected the proof"   # :178
+        finally:
+            free = getattr(self.protocol, "free", None)
+            if free is not None:
+                free(pkey)
+        return pkey, vkey, proof
