@@ -19,7 +19,7 @@ every Fp12 inversion from the Miller loop.
 
 from __future__ import annotations
 
-from .bls12_381 import P, R, G1, G2, f2_add, f2_sub, f2_mul, f2_inv, f2_neg
+from .bls12_381 import P, R, G1, G2, f2_add, f2_sub, f2_mul, f2_inv
 
 ATE_LOOP = 0xD201000000010000  # |z|
 FINAL_EXP = (P ** 12 - 1) // R

@@ -16,7 +16,7 @@ in sorted key order.
 
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 from .bls12_381 import R, G1, G2, Group, fr_inv

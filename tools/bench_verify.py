@@ -2,7 +2,6 @@
 """Latency of the verifier-side entry points (not a headline metric):
 zk_pairing_product at 1 / 3 / 4 pairs, Groth16 verify, and zk_g*_decompress throughput.
 Prints one JSON line."""
-import ctypes
 import json
 import os
 import sys

@@ -9,7 +9,7 @@ engine to exercise the sharding logic on CPU-only machines (never done in the pr
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 from . import _lib
 

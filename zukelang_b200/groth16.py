@@ -11,7 +11,7 @@ from __future__ import annotations
 import ctypes
 import random
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 from . import _lib, qap as Q
 from .curve import Bls12_381, Fr, Point, R, Var, fr_vector

@@ -31,9 +31,8 @@ interoperate — ``Groth16Wire.vkey_of_yojson`` can recompute it from ``pkey.a``
 
 from __future__ import annotations
 
-from typing import Any, Dict, List, Sequence, Tuple
+from typing import Any, Dict, List, Tuple
 
-from . import _lib
 from .curve import Bls12_381, GTElem, Point, R
 
 # ---- JSON over bytes ---------------------------------------------------------------------------
