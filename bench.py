@@ -18,6 +18,9 @@ Fields beyond the base contract:
                 kernel in the timed steps / the IMAD-chain peak measured in this same process.
   cpu_baseline  the oracle's C restatement of the reference's fold-MSM on the host cores
                 (bounded sample), rank 0 / N = 1 only.
+  cpu_pippenger informational "fair CPU" line: a multi-threaded bucket method in
+                portable C on the same host cores, checked against the fold; NOT the reference's
+                algorithm and not the baseline.
   e2e           same metric through the host-buffer C-ABI call (pinned host scalars in, point out).
 --impl reference runs only the CPU restatement (the reference itself needs OCaml, absent here).
 """
@@ -138,6 +141,9 @@ def load_c_oracle():
     lib = ctypes.CDLL(so)
     lib.zkoracle_g1_msm_fold.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
     lib.zkoracle_g1_msm_fold.restype = ctypes.c_int
+    lib.zkoracle_g1_msm_pippenger.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_void_p]
+    lib.zkoracle_g1_msm_pippenger.restype = ctypes.c_int
     return lib
 
 
@@ -148,6 +154,29 @@ def cpu_fold_msm(bases_raw, scalars_raw, n, threads):
     t0 = time.perf_counter()
     lib.zkoracle_g1_msm_fold(bases_raw, scalars_raw, n, threads, out)
     return time.perf_counter() - t0, bytes(out)
+
+
+def cpu_pippenger_msm(bases_raw, scalars_raw, n, threads, c=16):
+    """NOT the reference's algorithm: a plain multi-threaded bucket method in portable C (no assembly),
+    the "fair CPU" line of SURVEY.md §8(d); returns (seconds, out96)."""
+    lib = load_c_oracle()
+    out = (ctypes.c_uint8 * 96)()
+    t0 = time.perf_counter()
+    rc = lib.zkoracle_g1_msm_pippenger(bases_raw, scalars_raw, n, c, threads, out)
+    if rc != 0:
+        raise RuntimeError("zkoracle_g1_msm_pippenger: bad arguments")
+    return time.perf_counter() - t0, bytes(out)
+
+
+def cpu_pippenger_line(bases_raw, scalars_raw, n_check, fold_out, n_timed, threads):
+    """The informational ``cpu_pippenger`` object of the JSON line: checked against the fold on the
+    cpu_baseline sample, timed on a larger prefix of the same workload."""
+    _, chk = cpu_pippenger_msm(bases_raw[:n_check * 96], scalars_raw[:n_check * 32], n_check, threads)
+    secs, _ = cpu_pippenger_msm(bases_raw[:n_timed * 96], scalars_raw[:n_timed * 32], n_timed, threads)
+    return {"value": n_timed / secs / 1e6, "unit": "Mpts/s", "cores": threads, "window_bits": 16,
+            "agrees_with_fold": chk == fold_out,
+            "sample": "first %d of the 2^20 points, oracle/c bucket method (signed 16-bit windows, portable C, "
+                      "no assembly) on all host threads, %.1f s; not the reference's algorithm" % (n_timed, secs)}
 
 
 def oracle_bases(n, seed):
@@ -453,6 +482,13 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = {"value": sample / secs / 1e6, "unit": "Mpts/s", "cores": threads, "kind": "port",
                                     "sample": "first 2^15 of the 2^20 points, oracle/c fold of double-and-add scalar muls "
                                               "(curve.ml:91-118) on all host threads, %.1f s" % secs}
+            try:                                                   # informational; never lose the headline line
+                n_timed = min(1 << 18, n_total)
+                line["cpu_pippenger"] = cpu_pippenger_line(bases[:n_timed * 96].tobytes(),
+                                                           batches[0]["host"].numpy().tobytes()[:n_timed * 32],
+                                                           sample, out, n_timed, threads)
+            except Exception as e:
+                line["cpu_pippenger"] = {"error": repr(e)}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     _lib.check(zk.zk_table_free(handle.value))
     if dist is not None:

@@ -11,6 +11,11 @@
  * bls12-381 package does per call) plus one addition per term.  The reference is
  * single-threaded; `threads` > 1 splits the index range into contiguous chunks, folds each
  * chunk on its own thread and adds the partial sums — the same arithmetic, all host cores.
+ *
+ * Second entry point, NOT the reference's algorithm: zkoracle_g1_msm_pippenger, a plain
+ * multi-threaded bucket method (signed c-bit digits, mixed additions, running-sum bucket
+ * reduction) — the "fair CPU" line of SURVEY.md §8(d): what a CPU does with the same algorithm
+ * family the GPU path uses.  Reported beside cpu_baseline, never as it.
  */
 #include <pthread.h>
 #include <stdint.h>
@@ -165,6 +170,114 @@ int zkoracle_g1_msm_fold(const uint8_t *bases, const uint8_t *scalars, size_t n,
   for (int t = 0; t < threads; t++) { if (threads > 1) pthread_join(th[t], NULL); g1_add(&acc, &jobs[t].acc, &acc); }
   g1_to_raw(out, &acc);
   free(jobs); free(th);
+  return 0;
+}
+
+/* ---- "fair CPU" bucket method ------------------------------------------------------------ */
+/* r = p + (x2, y2) with the addend affine (madd-2007-bl: 7M + 4S); handles p = inf, p = +-q */
+static void g1_madd(g1 *r, const g1 *p, const fp *x2, const fp *y2) {
+  if (g1_is_inf(p)) { r->X = *x2; r->Y = *y2; r->Z = ONE; return; }
+  fp Z1Z1, U2, S2, H, HH, I, J, rr, V, t;
+  fp_sqr(&Z1Z1, &p->Z); fp_mul(&U2, x2, &Z1Z1);
+  fp_mul(&S2, y2, &p->Z); fp_mul(&S2, &S2, &Z1Z1);
+  if (fp_eq(&U2, &p->X)) {
+    if (fp_eq(&S2, &p->Y)) { g1 q; q.X = *x2; q.Y = *y2; q.Z = ONE; g1_dbl(r, &q); } else g1_set_inf(r);
+    return;
+  }
+  fp_sub(&H, &U2, &p->X); fp_sqr(&HH, &H); fp_add(&I, &HH, &HH); fp_add(&I, &I, &I); fp_mul(&J, &H, &I);
+  fp_sub(&rr, &S2, &p->Y); fp_add(&rr, &rr, &rr); fp_mul(&V, &p->X, &I);
+  fp X3, Y3, Z3;
+  fp_sqr(&X3, &rr); fp_sub(&X3, &X3, &J); fp_sub(&X3, &X3, &V); fp_sub(&X3, &X3, &V);
+  fp_sub(&t, &V, &X3); fp_mul(&Y3, &rr, &t); fp_mul(&t, &p->Y, &J); fp_add(&t, &t, &t); fp_sub(&Y3, &Y3, &t);
+  fp_add(&Z3, &p->Z, &H); fp_sqr(&Z3, &Z3); fp_sub(&Z3, &Z3, &Z1Z1); fp_sub(&Z3, &Z3, &HH);
+  r->X = X3; r->Y = Y3; r->Z = Z3;
+}
+
+typedef struct { fp x, y; int inf; } g1aff;
+typedef struct {
+  const g1aff *pts; const int32_t *digits;   /* digits[i * W + w], signed, |d| <= 2^(c-1) */
+  size_t lo, hi; int w, W, c; g1 acc;
+} pjob;
+
+/* one (window, point range) job: fill 2^(c-1) buckets, reduce them with the running sum */
+static void *pippenger_job(void *arg) {
+  pjob *j = (pjob *)arg;
+  const size_t nb = (size_t)1 << (j->c - 1);
+  g1 *bk = (g1 *)calloc(nb + 1, sizeof(g1));                    /* Z = 0: identity */
+  for (size_t i = j->lo; i < j->hi; i++) {
+    int32_t d = j->digits[i * j->W + j->w];
+    if (d == 0 || j->pts[i].inf) continue;
+    fp y = j->pts[i].y;
+    if (d < 0) { fp z; memset(&z, 0, sizeof z); fp_sub(&y, &z, &y); d = -d; }
+    g1_madd(&bk[d], &bk[d], &j->pts[i].x, &y);
+  }
+  g1 run, sum; g1_set_inf(&run); g1_set_inf(&sum);
+  for (size_t b = nb; b >= 1; b--) { g1_add(&run, &run, &bk[b]); g1_add(&sum, &sum, &run); }
+  free(bk);
+  j->acc = sum;
+  return NULL;
+}
+
+typedef struct { pjob *jobs; int first, step, count; } pworker;
+static void *pippenger_worker(void *arg) {
+  pworker *w = (pworker *)arg;
+  for (int k = w->first; k < w->count; k += w->step) pippenger_job(&w->jobs[k]);
+  return NULL;
+}
+
+/* out = sum_i scalars[i] * bases[i] by the bucket method with c-bit signed windows (2 <= c <= 20);
+ * returns 0, or -1 on a bad argument */
+int zkoracle_g1_msm_pippenger(const uint8_t *bases, const uint8_t *scalars, size_t n, int c, int threads,
+                              uint8_t out[96]) {
+  if (c < 2 || c > 20 || n == 0) return -1;
+  if (threads < 1) threads = 1;
+  const int W = (255 + c) / c;                                  /* room for the carry out of bit 254 */
+  g1aff *pts = (g1aff *)malloc(n * sizeof(g1aff));
+  int32_t *digits = (int32_t *)malloc(n * (size_t)W * sizeof(int32_t));
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t *b = bases + 96 * i;
+    pts[i].inf = (b[0] & 0x40) != 0;
+    if (!pts[i].inf) { fp_from_be(&pts[i].x, b); fp_from_be(&pts[i].y, b + 48); }
+    const uint8_t *k = scalars + 32 * i;
+    int carry = 0;
+    for (int w = 0; w < W; w++) {
+      int64_t v = carry;
+      for (int t = 0; t < c; t++) {
+        int bit = w * c + t;
+        if (bit < 256) v += (int64_t)((k[bit >> 3] >> (bit & 7)) & 1) << t;
+      }
+      carry = 0;
+      if (v > ((int64_t)1 << (c - 1))) { v -= (int64_t)1 << c; carry = 1; }
+      digits[i * W + w] = (int32_t)v;
+    }
+  }
+  /* W windows x `chunks` point ranges, so that every thread has work when threads > W */
+  int chunks = (threads + W - 1) / W;
+  if ((size_t)chunks > n) chunks = (int)n;
+  const int njobs = W * chunks;
+  pjob *jobs = (pjob *)calloc(njobs, sizeof(pjob));
+  for (int w = 0; w < W; w++)
+    for (int ch = 0; ch < chunks; ch++) {
+      pjob *j = &jobs[w * chunks + ch];
+      j->pts = pts; j->digits = digits; j->w = w; j->W = W; j->c = c;
+      j->lo = n * (size_t)ch / chunks; j->hi = n * (size_t)(ch + 1) / chunks;
+    }
+  if (threads > njobs) threads = njobs;
+  pthread_t *th = (pthread_t *)calloc(threads, sizeof(pthread_t));
+  pworker *wk = (pworker *)calloc(threads, sizeof(pworker));
+  for (int t = 0; t < threads; t++) {
+    wk[t].jobs = jobs; wk[t].first = t; wk[t].step = threads; wk[t].count = njobs;
+    if (threads == 1) pippenger_worker(&wk[t]); else pthread_create(&th[t], NULL, pippenger_worker, &wk[t]);
+  }
+  if (threads > 1) for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  /* Horner over the windows, most significant first */
+  g1 acc; g1_set_inf(&acc);
+  for (int w = W - 1; w >= 0; w--) {
+    for (int t = 0; t < c; t++) g1_dbl(&acc, &acc);
+    for (int ch = 0; ch < chunks; ch++) g1_add(&acc, &acc, &jobs[w * chunks + ch].acc);
+  }
+  g1_to_raw(out, &acc);
+  free(jobs); free(th); free(wk); free(pts); free(digits);
   return 0;
 }
 

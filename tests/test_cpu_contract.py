@@ -48,3 +48,17 @@ def test_ocaml_stubs_compile_against_the_c_abi():
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-Wno-unused-parameter", "-fsyntax-only",
                            "-I", os.path.join(ROOT, "tests", "ocaml_mock"), "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "ocaml", "zkb200_stubs.c")])
+
+
+def test_bench_cpu_legs_agree():
+    """bench.py's two host-side legs on a small prefix: the reference's fold (cpu_baseline) and the
+    informational bucket method (cpu_pippenger) give the same point."""
+    import bench
+    n = 96
+    bases_raw, _dl = bench.oracle_bases(n, 7)
+    _w, ints = bench.uniform_scalars(n, 11)
+    sc_raw = b"".join(v.to_bytes(32, "little") for v in ints)
+    _secs, fold = bench.cpu_fold_msm(bases_raw[:64 * 96], sc_raw[:64 * 32], 64, 4)
+    line = bench.cpu_pippenger_line(bases_raw, sc_raw, 64, fold, n, 4)
+    assert line["agrees_with_fold"] is True and line["value"] > 0 and line["unit"] == "Mpts/s"
+    assert line["cores"] == 4 and "not the reference's algorithm" in line["sample"]
