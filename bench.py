@@ -141,9 +141,10 @@ def load_c_oracle():
     lib = ctypes.CDLL(so)
     lib.zkoracle_g1_msm_fold.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
     lib.zkoracle_g1_msm_fold.restype = ctypes.c_int
-    lib.zkoracle_g1_msm_pippenger.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
-                                              ctypes.c_int, ctypes.c_void_p]
-    lib.zkoracle_g1_msm_pippenger.restype = ctypes.c_int
+    if hasattr(lib, "zkoracle_g1_msm_pippenger"):         # absent from a stale build: only cpu_pippenger is lost
+        lib.zkoracle_g1_msm_pippenger.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_void_p]
+        lib.zkoracle_g1_msm_pippenger.restype = ctypes.c_int
     return lib
 
 
