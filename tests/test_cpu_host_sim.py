@@ -244,3 +244,33 @@ def test_square_roots_and_subgroup_check(simp):
             break
         x += 1
     assert simp.sim_in_subgroup(0, (ctypes.c_uint32 * 24)(*_enc_aff(G1, (x, y), 12))) == 0
+
+
+# ---- experimental FP64-pipe Montgomery product (csrc/exp/mont_f64.cuh; round-2 candidate) --------
+def test_f64_limb_product_montgomery():
+    out = tempfile.mkdtemp(prefix="zk_host_sim_")
+    so = os.path.join(out, "sim_f64.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-DZK_HOST_SIM", "-shared", "-fPIC", "-x", "c++",
+                           os.path.join(SIM, "sim_f64.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.sim_f64_fma_rz.restype = ctypes.c_double
+    lib.sim_f64_fma_rz.argtypes = [ctypes.c_double] * 3
+    # the emulated fma.rz.f64 itself: exact a*b + c truncated toward zero to 53 bits
+    rng = random.Random(31)
+    for _ in range(2000):
+        a, b = rng.getrandbits(48), rng.getrandbits(48)
+        hi = lib.sim_f64_fma_rz(float(a), float(b), float(1 << 104))
+        assert int(hi) - (1 << 104) == (a * b >> 52) << 52
+        lo = lib.sim_f64_fma_rz(float(a), float(b), float((1 << 104) + (1 << 52)) - hi)
+        assert int(lo) - (1 << 52) == a * b & ((1 << 52) - 1)
+    l48 = lambda x: (ctypes.c_uint64 * 8)(*[(x >> (48 * i)) & ((1 << 48) - 1) for i in range(8)])
+    n0 = (-pow(P, -1, 1 << 48)) % (1 << 48)
+    Ri = pow(1 << 384, -1, P)
+    vals = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (1 << 380) % P, RM] + [rng.randrange(P) for _ in range(3000)]
+    o = (ctypes.c_uint64 * 8)()
+    for i, a in enumerate(vals):
+        b = vals[(i * 13 + 5) % len(vals)]
+        lib.sim_f64_mul(l48(a), l48(b), l48(P), ctypes.c_uint64(n0), o)
+        got = sum(int(o[k]) << (48 * k) for k in range(8))
+        assert all(int(o[k]) < (1 << 48) for k in range(8))
+        assert got == a * b * Ri % P, (hex(a), hex(b))
