@@ -55,3 +55,26 @@ def test_compression_of_uncompressed_bytes_matches_the_oracle():
         pts += [G.neg(p) for p in pts[3:]]
         for p in pts:
             assert Gm.to_compressed_bytes(Point(unc(p))) == comp(p)
+
+
+def test_qap_build_matches_the_reference_restatement():
+    """Host mirror of QAP.build (shared barycentric basis) against the oracle's literal restatement
+    of QAP.ml:18-94 (one Polynomial.interpolate per variable) — no device needed."""
+    from oracle import zk as Z
+    from zukelang_b200 import qap as Q
+    from zukelang_b200.protocol import Circuit, Gate, gate_set
+    for (circ, _wit), literal in ((Z.circuit_cubic(), True), (Z.circuit_pair_case(7), True),
+                                  (Z.circuit_mulchain(9), True), (Z.circuit_pair_case(40), False)):
+        oq = Z.qap_build(circ.gates, literal=literal)
+        gates = [Gate.make(dict(g.lhs), dict(g.l), dict(g.r)) for g in reversed(circ.gates)]   # any input order
+        q, rgs = Q.build(gates + gates[:1])                                                     # duplicates collapse
+        assert [r for r, _ in rgs] == list(range(len(circ.gates)))
+        assert [(g.lhs, g.l, g.r) for _, g in rgs] == [(g.lhs, g.l, g.r) for g in circ.gates]   # Gate.Set order
+        assert q.target == list(oq.target) and q.n == len(circ.gates)
+        for name in ("v", "w", "y"):
+            got, exp = getattr(q, name), getattr(oq, name)
+            assert set(got) == set(exp)
+            for k in exp:
+                assert got[k] == list(exp[k]), (name, k)
+        c = Circuit.of_gates(gates, circ.inputs_public, circ.outputs, circ.mids)
+        assert list(c.vars) == circ.vars() and c.ios() == circ.ios() and list(c.gates) == gate_set(gates)
