@@ -78,3 +78,11 @@ def test_qap_build_matches_the_reference_restatement():
                 assert got[k] == list(exp[k]), (name, k)
         c = Circuit.of_gates(gates, circ.inputs_public, circ.outputs, circ.mids)
         assert list(c.vars) == circ.vars() and c.ios() == circ.ios() and list(c.gates) == gate_set(gates)
+
+
+@pytest.mark.parametrize("doc", [b'{"a":"x"}', b'[1,2]', b'{"a":1,"b":2,"c":3}', b'"str"'])
+def test_documents_of_the_wrong_shape_are_rejected(doc):
+    with pytest.raises(ValueError):
+        wire.decode(wire.Groth16Wire.PROOF, wire.loads(doc))
+    with pytest.raises(ValueError):
+        wire.decode(wire.Map_("Fr"), wire.loads(b'[["x","1"]]'))

@@ -290,7 +290,10 @@ def decode(schema, j, C=Bls12_381):
     """JSON structure (from ``loads``) -> value; records come back as dicts.  Points are
     decompressed — and checked: encoding, curve, subgroup — in one device call per group."""
     pend = _Pending()
-    v = _decode(schema, j, pend)
+    try:
+        v = _decode(schema, j, pend)
+    except (KeyError, IndexError, TypeError, AttributeError) as e:        # wrong shape for the schema
+        raise ValueError("wire.decode: document does not match the schema (%r)" % (e,)) from None
     for G, pts in ((C.G1, pend.g1), (C.G2, pend.g2)):
         for p, full in zip(pts, G.of_compressed_bytes_many([p._comp for p in pts])):
             p.raw = full.raw
