@@ -100,6 +100,11 @@ int zk_table_join(uint64_t handle, void *cuda_stream);
  * receives the last profiled run's times once that stream has been synchronised:
  * [0] digits + scan + scatter, [1] bucket accumulation, [2] bucket reduction, [3] window combine. */
 int zk_table_profile(uint64_t handle, int enable, float stage_ms[4]);
+/* Per-step timing of zk_g*_table_msm_batch (bench.py's e2e leg): enable != 0 makes the following
+ * batch calls on this table record, for each of their first 64 steps, when its upload started and
+ * ended (copy stream) and when its first and last kernel ran (compute stream).  out (nullable, with
+ * steps) receives 4 floats per step of the LAST batch call, in ms since its first upload started. */
+int zk_table_batch_timing(uint64_t handle, int enable, float *out, size_t cap, size_t *steps);
 int zk_table_free(uint64_t handle);
 
 /* ---- sum of k points (combining the shards' partial results) ------
@@ -251,8 +256,14 @@ int zk_bench_intpipe(int kind, int iters, double *ops_per_s, double *elapsed_ms)
 
 /* Device unit-test hook: applies op to n operand pairs of field elements given as raw
  * little-endian 32-bit limbs (tests/test_device_field.py).  field: 0 = Fp (12 limbs),
- * 1 = Fr (8 limbs).  op: 0 mul, 1 add, 2 sub, 3 neg, 4 to_mont, 5 from_mont, 6 inverse, 7 dbl. */
+ * 1 = Fr (8 limbs).  op: 0 mul, 1 add, 2 sub, 3 neg, 4 to_mont, 5 from_mont, 6 inverse, 7 dbl,
+ * 8 sqr (the dedicated Montgomery square of the bucket accumulation), 9 / 10 = first / second
+ * result of the interleaved pair mul2(a, b, a + b, a - b). */
 int zk_test_field_op(int field, int op, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n);
+/* Device unit-test hook for the mixed addition of the bucket accumulation: out[i] = 2 p[i] + q[i]
+ * (n uncompressed G1 points each; out = n point results).  variant: 0 = madd, 1 = madd_paired
+ * (interleaved products, what k_accumulate runs), 2 = general XYZZ add. */
+int zk_test_g1_madd(const uint8_t *p, const uint8_t *q, int variant, size_t n, uint8_t *out);
 
 #ifdef __cplusplus
 }

@@ -502,6 +502,64 @@ def groth16_closed_form(td: Groth16Trapdoor, r: int, s: int, qap: QAP, circuit: 
     return G1.of_Fr(A), G2.of_Fr(B), G1.of_Fr(C)
 
 
+def _batch_inverse(xs: Sequence[int]) -> List[int]:
+    pre, acc = [], 1
+    for x in xs:
+        pre.append(acc)
+        acc = acc * x % R
+    inv = fr_inv(acc)
+    out = [0] * len(xs)
+    for i in range(len(xs) - 1, -1, -1):
+        out[i] = inv * pre[i] % R
+        inv = inv * xs[i] % R
+    return out
+
+
+def lagrange_values_at(n: int, t: int) -> Tuple[List[int], int]:
+    """([L_j(t)] for j < n, Z(t)) on the reference's domain 0..n-1 (QAP.ml:84,92) for a point t
+    outside it: the polynomials poly_lagrange_basis (polynomial.ml:212-230) builds, evaluated by
+    L_j(t) = Z(t) / ((t - j) prod_{i != j} (j - i)) — O(n), usable at 2^20 gates."""
+    fact = [1] * n
+    for i in range(1, n):
+        fact[i] = fact[i - 1] * i % R
+    dens, z = [], 1
+    for j in range(n):
+        d = fact[j] * fact[n - 1 - j] % R            # |prod_{i != j} (j - i)|, sign (-1)^(n-1-j)
+        if (n - 1 - j) & 1:
+            d = R - d
+        dens.append(d * ((t - j) % R) % R)
+        z = z * ((t - j) % R) % R
+    assert z != 0, "t lies on the evaluation domain"
+    return [z * i % R for i in _batch_inverse(dens)], z
+
+
+def groth16_closed_form_scalars(td: Groth16Trapdoor, r: int, s: int, circuit: Circuit,
+                                sol: Dict[Var, int]) -> Tuple[int, int, int]:
+    """The trapdoor identity of groth16_closed_form computed from the GATE LIST alone (no dense
+    QAP.t, which cannot exist at 2^16+ gates): v_k(t) = sum_j l_j[k] L_j(t) by
+    QAP.ml:81-86, so V(t) = sum_j <l_j, sol> L_j(t) and likewise W, Y and the mid-variable sum L.
+    Returns the scalars (A, B, C) of the generators; O(n + nnz)."""
+    lag, zt = lagrange_values_at(len(circuit.gates), td.t)
+    mid = set(circuit.mids)
+    V = W = Y = L = 0
+    for g, lj in zip(circuit.gates, lag):
+        vj, wj, yj = affine_eval(sol, g.l), affine_eval(sol, g.r), affine_eval(sol, g.lhs)
+        V += vj * lj
+        W += wj * lj
+        Y += yj * lj
+        lm = sum(td.b * c * sol[k] for k, c in g.l if k in mid)
+        lm += sum(td.a * c * sol[k] for k, c in g.r if k in mid)
+        lm += sum(c * sol[k] for k, c in g.lhs if k in mid)
+        L += lm % R * lj
+    V, W, Y, L = V % R, W % R, Y % R, L % R
+    dinv = fr_inv(td.d)
+    H = (V * W - Y) * fr_inv(zt) % R
+    A = (td.a + V + r * td.d) % R
+    B = (td.b + W + s * td.d) % R
+    C = (L * dinv + H * zt * dinv + s * A + r * B - r * s * td.d) % R
+    return A, B, C
+
+
 # ==========================================================================
 # pinocchio/pinocchio.ml
 # ==========================================================================
@@ -750,6 +808,44 @@ def circuit_pair_case(n_gates: int, seed: int = 0x50494E4F) -> Tuple[Circuit, ca
     return circ, witness
 
 
+def circuit_random_r1cs(n: int, seed: int = 0x47524F54) -> Tuple[Circuit, callable]:
+    """Config 5's alternative workload: a seeded random sparse R1CS of n gates,
+    gate i:  z_i = (a x_p + b x_q + k ONE) * (c x_s + d x_u)  with p, q, s, u drawn among the
+    variables defined before gate i and a, b, c, d, k uniform in Fr (about 3 non-zeros per row of
+    each of the l / r matrices' union).  Unlike the multiply chain, W(j) differs at every gate, so
+    the G2 B-query sees uniformly spread scalars.  Satisfiable by construction: the witness
+    evaluates the gates in order."""
+    import random
+    rng = random.Random(seed + n)
+    xs = [("input", 2), ("input", 3)]
+    zs = [("_tmp", 4 + i) for i in range(n - 1)] + [("v", 3 + n)]
+    defined = list(xs)
+    gates, plan = [], []
+    for i in range(n):
+        p, q, s_, u = (defined[rng.randrange(len(defined))] for _ in range(4))
+        a, b, c, d, k = (rng.randrange(1, R) for _ in range(5))
+        l, r = {}, {}
+        for var, co in ((p, a), (q, b), (ONE, k)):
+            l[var] = (l.get(var, 0) + co) % R
+        for var, co in ((s_, c), (u, d)):
+            r[var] = (r.get(var, 0) + co) % R
+        gates.append(Gate.make({zs[i]: 1}, l, r))
+        plan.append((zs[i], sorted(l.items()), sorted(r.items())))
+        defined.append(zs[i])
+    circ = Circuit(gates, inputs_public=[ONE], outputs=[zs[-1]], mids=xs + zs[:-1])
+    assert len(circ.gates) == n
+
+    def witness(seed2: int) -> Dict[Var, int]:
+        r2 = random.Random(seed2)
+        sol = {ONE: 1, xs[0]: r2.randrange(R), xs[1]: r2.randrange(R)}
+        for z, l, r in plan:
+            sol[z] = sum(c * sol[v] for v, c in l) % R * (sum(c * sol[v] for v, c in r) % R) % R
+        live = set(circ.vars())
+        return {k: v for k, v in sol.items() if k in live}
+
+    return circ, witness
+
+
 def self_check() -> None:
     polynomial_self_test()
     circ, wit = circuit_cubic()
@@ -769,6 +865,12 @@ def self_check() -> None:
     bad = dict(pub)
     bad[ONE] = 2
     assert not groth16_verify(bad, vk, proof)
+    # the gate-list closed form (used at sizes with no dense QAP) equals the dense one
+    for c2, w2 in (circuit_cubic(), circuit_mulchain(9), circuit_random_r1cs(12)):
+        s2 = w2(5)
+        assert circuit_check(c2, s2)
+        A, B, C = groth16_closed_form_scalars(td, 101, 202, c2, s2)
+        assert (G1.of_Fr(A), G2.of_Fr(B), G1.of_Fr(C)) == groth16_closed_form(td, 101, 202, qap_build(c2.gates), c2, s2)
 
 
 if __name__ == "__main__":

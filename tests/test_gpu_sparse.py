@@ -28,7 +28,7 @@ def test_sparse_path_equals_dense_path_and_oracle(zk, name, n):
     sc = _sparse(circ)
     dom = S.EvalDomain(sc)
     P = S.Groth16Sparse()
-    pk, vk, td = P.keygen(random.Random(n), sc, dom.w)
+    pk, vk, td = P.keygen_with_trapdoor(random.Random(n), sc, dom.w)
     otd = Z.Groth16Trapdoor(*td)
     opk, ovk = Z.groth16_keygen(otd, circ, oq, with_ab=(n <= 8))
     # the reference-shaped fields of the derived key equal the oracle's
@@ -65,7 +65,7 @@ def test_sparse_groth16_4096_closed_form(zk):
     sc = _sparse(circ)
     dom = S.EvalDomain(sc)
     P = S.Groth16Sparse()
-    pk, vk, td = P.keygen(random.Random(7), sc, dom.w)
+    pk, vk, td = P.keygen_with_trapdoor(random.Random(7), sc, dom.w)
     sol = wit(0xC0FFEE)
     r, s = 123456789, 987654321
     proof = P.prove_with(r, s, dom, pk, sol)

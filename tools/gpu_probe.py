@@ -82,6 +82,13 @@ def msm_run(zk, group, logn, precompute, iters, c, seed=0x5A554B45, dist="unifor
         torch.cuda.synchronize()
         if it:
             times.append(e0.elapsed_time(e1))
+    # stage split of one more run (digits+sort, accumulate+fix-up, bucket reduction, finalize)
+    stage = (ctypes.c_float * 4)()
+    _lib.check(zk.zk_table_profile(h.value, 1, None))
+    with torch.cuda.stream(side):
+        _lib.check(msm_dev(h.value, d_sc.data_ptr(), n, d_out.data_ptr(), side.cuda_stream))
+    torch.cuda.synchronize()
+    _lib.check(zk.zk_table_profile(h.value, 0, stage))
     got = bytes(d_out.cpu().numpy())
     # exact check: sum s_i d_i mod r times the generator, via a 1-point MSM on the device
     tot = sum(a * b for a, b in zip(words_to_ints(sc_w), words_to_ints(dl_w))) % R
@@ -92,7 +99,8 @@ def msm_run(zk, group, logn, precompute, iters, c, seed=0x5A554B45, dist="unifor
     ms = min(times)
     print(json.dumps({"probe": "msm", "group": group, "log_n": logn, "precompute": precompute, "c": int(info[0]),
                       "W": int(info[1]), "S": int(info[4]), "table_MB": int(info[5]) >> 20, "ms": ms,
-                      "ms_all": times, "Mpts_per_s": n / ms / 1e3, "exact_ok": bool(ok), "scalars": dist,
+                      "ms_all": times, "stages_ms": [round(float(x), 4) for x in stage],
+                      "env": {k: v for k, v in os.environ.items() if k.startswith("ZKB200_") and k != "ZKB200_DEVICE"}, "Mpts_per_s": n / ms / 1e3, "exact_ok": bool(ok), "scalars": dist,
                       "fixed_base_s": t_fixed, "load_s": t_load}), flush=True)
     return ok
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "zk_table_pipeline": (c_int, [c_uint64, c_int]),
     "zk_table_join": (c_int, [c_uint64, c_void_p]),
     "zk_table_profile": (c_int, [c_uint64, c_int, c_void_p]),
+    "zk_table_batch_timing": (c_int, [c_uint64, c_int, c_void_p, c_size_t, POINTER(c_size_t)]),
     "zk_table_free": (c_int, [c_uint64]),
     "zk_g1_sum": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_g2_sum": (c_int, [c_void_p, c_size_t, c_void_p]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "zk_g2_decompress": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_bench_intpipe": (c_int, [c_int, c_int, POINTER(c_double), POINTER(c_double)]),
     "zk_test_field_op": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "zk_test_g1_madd": (c_int, [c_void_p, c_void_p, c_int, c_size_t, c_void_p]),
 }
 
 class Groth16PKeyStruct(ctypes.Structure):

@@ -133,14 +133,59 @@ __global__ void k_test_field_op(int op, const uint32_t* a, const uint32_t* b, ui
     case 5: r = x.from_mont(); break;
     case 6: r = x.inverse(); break;
     case 7: r = x.dbl(); break;
+    case 8: r = x.sqr(); break;                                   // dedicated square (Fp) / plain product (Fr)
+    case 9: case 10: {                                            // interleaved pair: (x y, (x + y)(x - y))
+      F r1, r2;
+      F::mul2(x, y, x + y, x - y, r1, r2);
+      r = op == 9 ? r1 : r2;
+      break;
+    }
     default: r = F::zero();
   }
   for (int j = 0; j < F::N; j++) out[(size_t)i * F::N + j] = r.v[j];
 }
 
+// ---- device mixed-add test hook ------------------------------------------------------
+// out[i] = 2 p[i] + q[i] through the bucket-accumulation formulas: the accumulator 2 p has
+// ZZ != 1, q is the affine addend.  variant 0 = XYZZ::madd, 1 = XYZZ::madd_paired (the one
+// k_accumulate<Fp> runs), 2 = general XYZZ::add of from_affine(q).
+__global__ void k_test_g1_madd(const uint8_t* __restrict__ p, const uint8_t* __restrict__ q, int variant, uint32_t n,
+                               uint8_t* __restrict__ out, int* __restrict__ err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine a, b;
+  if (G1Traits::parse(p + (size_t)i * 96, a) || G1Traits::parse(q + (size_t)i * 96, b)) { atomicExch(err, 1); return; }
+  G1XYZZ acc = G1XYZZ::dbl_affine(a);
+  if (variant == 0) acc.madd(b);
+  else if (variant == 1) acc.madd_paired(b);
+  else acc.add(G1XYZZ::from_affine(b));
+  G1Affine r = acc.to_affine();
+  G1Traits::serialize(r, out + (size_t)i * (96 + 48));
+}
+
 }  // namespace zk
 
 extern "C" {
+
+int zk_test_g1_madd(const uint8_t* p, const uint8_t* q, int variant, size_t n, uint8_t* out) {
+  ZK_API_BEGIN
+  using namespace zk;
+  ZK_REQUIRE(p && q && out && n > 0 && n < (1u << 24) && variant >= 0 && variant <= 2, ZK_EARG, "test_g1_madd: bad arguments");
+  cudaStream_t st = default_stream();
+  DevBuf<uint8_t> dp(n * 96), dq(n * 96), dout(n * 144);
+  DevBuf<int> derr(1);
+  ZK_CUDA(cudaMemcpyAsync(dp.p, p, n * 96, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(dq.p, q, n * 96, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+  k_test_g1_madd<<<cdiv(n, 64), 64, 0, st>>>(dp.p, dq.p, variant, (uint32_t)n, dout.p, derr.p);
+  ZK_CUDA(cudaGetLastError());
+  int err = 0;
+  ZK_CUDA(cudaMemcpyAsync(out, dout.p, n * 144, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(err == 0, ZK_EPOINT, "test_g1_madd: point not canonical or not on the curve");
+  ZK_API_END
+}
 
 int zk_bench_intpipe(int kind, int iters, double* ops_per_s, double* elapsed_ms) {
   ZK_API_BEGIN
@@ -217,6 +262,17 @@ int zk_table_profile(uint64_t handle, int enable, float stage_ms[4]) {
     if (stage_ms) h->table.stage_ms(stage_ms);
     h->table.profile = enable != 0;
   }
+  ZK_API_END
+}
+
+int zk_table_batch_timing(uint64_t handle, int enable, float* out, size_t cap, size_t* steps) {
+  ZK_API_BEGIN
+  using namespace zk;
+  HandleBase* hb = lookup_handle(handle, 0);
+  ZK_REQUIRE(hb->kind == 1 || hb->kind == 2, ZK_EARG, "table_batch_timing: not a table handle");
+  ZK_REQUIRE((out == nullptr) == (steps == nullptr), ZK_EARG, "table_batch_timing: out and steps go together");
+  if (hb->kind == 1) api_table_batch_timing<G1Traits>(static_cast<TableHandle<G1Traits>*>(hb), enable, out, cap, steps);
+  else api_table_batch_timing<G2Traits>(static_cast<TableHandle<G2Traits>*>(hb), enable, out, cap, steps);
   ZK_API_END
 }
 

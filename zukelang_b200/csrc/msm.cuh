@@ -23,6 +23,7 @@
 // disappears, at the price of W times the table bytes — cheap against 180 GB of HBM3e.
 // (msm_ba.cuh holds an experimental batched-affine accumulation, off by default.)
 #pragma once
+#include <exception>
 #include "common.cuh"
 
 namespace zk {
@@ -186,14 +187,31 @@ k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __rest
 // partial[2t] (slice starts inside that bucket) / partial[2t+1] (bucket runs past the slice end) and
 // k_fix_partials adds them up.  Bases are gathered with 128-bit loads, the next base is fetched
 // while the current one is added.
-// MINB = resident blocks per SM the register allocation is capped for; PREFETCH = fetch the
-// next base while adding the current one (costs 24 registers); PAIRED = mixed add with its
-// independent products issued as interleaved pairs (Fp only; wants the registers of MINB = 2).
-template <class F, int MINB, bool PREFETCH, bool PAIRED = false>
-__global__ void __launch_bounds__(128, MINB)
+// MINB = resident blocks per SM the register allocation is capped for; STAGED = the next base is
+// fetched by cp.async (LDGSTS) into a per-thread shared-memory slot while the current one is being
+// added: the gather latency (entry -> base, two dependent DRAM accesses) disappears behind the
+// ~13 us of a mixed add without costing the 24-48 registers a register prefetch would; PAIRED =
+// mixed add with its independent products issued as interleaved pairs (Fp only; wants the
+// registers of MINB = 2).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int ACC_THREADS = 128;
+template <class F>
+constexpr size_t acc_stage_bytes() { return 2 * sizeof(Affine<F>) * ACC_THREADS; }   // double-buffered slot per thread
+
+template <class F, int MINB, bool STAGED, bool PAIRED = false>
+__global__ void __launch_bounds__(ACC_THREADS, MINB)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums, XYZZ<F>* __restrict__ partial,
              uint32_t nbuckets) {
+  extern __shared__ uint4 acc_stage[];   // [2][VEC][ACC_THREADS] when STAGED: conflict-free 16-byte columns
+  constexpr int VEC = sizeof(Affine<F>) / 16;
   const uint32_t T = gridDim.x * blockDim.x;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t E = offsets[nbuckets];
@@ -202,6 +220,18 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
   if (per == 0 || e0_64 >= E) return;
   const uint32_t e0 = (uint32_t)e0_64;
   const uint32_t e1 = min(E, e0 + per);
+  auto issue = [&](int buf, uint32_t ent) {
+    const uint4* src = reinterpret_cast<const uint4*>(&bases[ent & 0x7fffffffu]);
+#pragma unroll
+    for (int j = 0; j < VEC; j++) cp_async16(&acc_stage[(buf * VEC + j) * ACC_THREADS + threadIdx.x], src + j);
+    cp_async_commit();
+  };
+  uint32_t e = entries[e0];
+  uint32_t e_next = 0;
+  if (STAGED) {
+    issue(0, e);
+    if (e0 + 1 < e1) e_next = entries[e0 + 1];
+  }
   // bucket of entry e0: largest b with offsets[b] <= e0
   uint32_t lo = 0, hi = nbuckets;
   while (hi - lo > 1) {
@@ -213,29 +243,39 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
   while (b_end <= e0) { b++; b_end = offsets[b + 1]; }   // skip empty buckets sharing the offset
   uint32_t seg_start = e0;
   XYZZ<F> acc = XYZZ<F>::inf();
-  uint32_t e = entries[e0];
   Affine<F> cur;
-  if (PREFETCH) cur = load_vec(&bases[e & 0x7fffffffu]);
   for (uint32_t k = e0; k < e1; k++) {
-    if (k >= b_end) {  // bucket b is finished: it started at seg_start
-      const bool complete = seg_start == offsets[b];
-      store_vec(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);   // incomplete => started before e0
-      acc = XYZZ<F>::inf();
-      do { b++; b_end = offsets[b + 1]; } while (b_end <= k);
-      seg_start = k;
-    }
-    if (PREFETCH) {
-      uint32_t e_next = 0;
-      Affine<F> nxt;
+    if (STAGED) {
+      // base k + 1 starts travelling now; the index of base k + 2 is fetched one iteration early so
+      // that issuing a copy never waits on its address
+      const int buf = (int)((k - e0) & 1);
       const bool more = k + 1 < e1;
-      if (more) {
-        e_next = entries[k + 1];
-        nxt = load_vec(&bases[e_next & 0x7fffffffu]);
+      if (more) issue(buf ^ 1, e_next);
+      uint32_t e_next2 = 0;
+      if (k + 2 < e1) e_next2 = entries[k + 2];
+      if (k >= b_end) {  // bucket b is finished: it started at seg_start
+        const bool complete = seg_start == offsets[b];
+        store_vec(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);   // incomplete => started before e0
+        acc = XYZZ<F>::inf();
+        do { b++; b_end = offsets[b + 1]; } while (b_end <= k);
+        seg_start = k;
       }
+      if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+      uint4* c4 = reinterpret_cast<uint4*>(&cur);
+#pragma unroll
+      for (int j = 0; j < VEC; j++) c4[j] = acc_stage[(buf * VEC + j) * ACC_THREADS + threadIdx.x];
       if (e >> 31) cur.y = cur.y.neg();
-      acc.madd(cur);
-      if (more) { cur = nxt; e = e_next; }
+      if constexpr (PAIRED) acc.madd_paired(cur); else acc.madd(cur);
+      e = e_next;
+      e_next = e_next2;
     } else {
+      if (k >= b_end) {
+        const bool complete = seg_start == offsets[b];
+        store_vec(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);
+        acc = XYZZ<F>::inf();
+        do { b++; b_end = offsets[b + 1]; } while (b_end <= k);
+        seg_start = k;
+      }
       e = entries[k];
       cur = load_vec(&bases[e & 0x7fffffffu]);
       if (e >> 31) cur.y = cur.y.neg();
@@ -504,8 +544,10 @@ struct BaseTable {
   // finishes them with ONE batched launch sequence on the caller's stream (flush / join).
   DevBuf<XYZZ<F>> bucket_sums, partial, chunk_out, tree_tmp, window_sums;   // MSM_QUEUE slots each (partial: 1)
   uint32_t acc_blocks = 0;   // persistent grid of k_accumulate: resident blocks per SM x SMs
-  int acc_variant = 0;       // ZKB200_ACC_VARIANT[_G2]: 8 (G1 default) paired products, 254 registers, 2 blocks/SM;
-                             // 1 plain, 128 registers, 4 blocks/SM; 4 (G2 default) plain, 255 registers
+  int acc_variant = 0;       // ZKB200_ACC_VARIANT[_G2]: see build_tables (9 / 5 = cp.async-staged defaults for G1 / G2)
+  template <class Fn> void acc_dispatch(Fn&& fn);
+  int acc_occupancy();
+  void acc_launch(uint32_t grid, XYZZ<F>* bsum, cudaStream_t st);
   int queued = 0;
   int queue_cap = 0;         // bucket buffers currently allocated (1 unless pipelined)
   TailOutputs<F> outs{};
@@ -530,6 +572,9 @@ struct BaseTable {
   // pipelined = queue up to MSM_QUEUE tails (allocates that many bucket buffers on first use)
   void set_pipelined(bool on);
   void ensure_queue(int slots);
+  // forget every queued tail (after an error between run() and join(): the queued output pointers
+  // may refer to buffers that are being unwound); the caller drains the streams first
+  void abort_queue() { queued = 0; }
   // stage timing (bench.py's roofline leg): when `profile` is set, run() brackets its stages with
   // CUDA events; stage_ms() reads them after the streams have drained.
   // stages: 0 digits+scan+scatter, 1 accumulate (+ partial fix-up), 2 bucket reduce, 3 combine+finalize
@@ -538,6 +583,27 @@ struct BaseTable {
   void stage_ms(float out[4]);
   ~BaseTable();
   size_t device_bytes() const;
+};
+
+// Pipelines a table for the lifetime of the scope.  If the scope is left by an exception while
+// tails are still queued, the device is drained and the queue dropped, so that a later run() /
+// join() on the handle never writes through output pointers of the failed call.
+template <class T>
+struct PipelineScope {
+  BaseTable<T>& t;
+  bool was;
+  int exc;
+  cudaStream_t extra;
+  explicit PipelineScope(BaseTable<T>& t_, cudaStream_t extra_ = nullptr)
+      : t(t_), was(t_.pipelined), exc(std::uncaught_exceptions()), extra(extra_) { t.set_pipelined(true); }
+  ~PipelineScope() {
+    if (std::uncaught_exceptions() > exc) {
+      cudaDeviceSynchronize();
+      if (extra) cudaStreamSynchronize(extra);
+      t.abort_queue();
+    }
+    t.pipelined = was;
+  }
 };
 
 template <class T>

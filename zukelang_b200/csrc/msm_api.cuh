@@ -5,6 +5,48 @@
 
 namespace zk {
 
+// Staging of zk_g*_table_msm_batch, owned by the handle: nothing is allocated, created or freed
+// per call (round 1 paid three cudaMalloc, four cudaEventCreate and three device-synchronising
+// cudaFree inside the timed call).
+constexpr int BATCH_TIMED_STEPS = 64;
+struct BatchStage {
+  DevBuf<uint32_t> d_sc[2];              // double-buffered scalar vectors
+  DevBuf<uint8_t> d_outs;                // count point results
+  cudaStream_t copy = nullptr;           // upload stream
+  cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+  // per-step timing (zk_table_batch_timing): upload start / end on the copy stream, first kernel /
+  // last kernel of the step on the compute stream
+  bool timed = false;
+  int steps_timed = 0;
+  cudaEvent_t t_c0[BATCH_TIMED_STEPS] = {}, t_c1[BATCH_TIMED_STEPS] = {}, t_k0[BATCH_TIMED_STEPS] = {},
+              t_k1[BATCH_TIMED_STEPS] = {};
+  void ensure(size_t n, size_t count, size_t out_bytes) {
+    d_sc[0].ensure(n * 8);
+    d_sc[1].ensure(n * 8);
+    d_outs.ensure(count * out_bytes);
+    if (!copy) {
+      ZK_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; b++) {
+        ZK_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+        ZK_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+      }
+    }
+    if (timed && !t_c0[0])
+      for (int i = 0; i < BATCH_TIMED_STEPS; i++) {
+        ZK_CUDA(cudaEventCreate(&t_c0[i])); ZK_CUDA(cudaEventCreate(&t_c1[i]));
+        ZK_CUDA(cudaEventCreate(&t_k0[i])); ZK_CUDA(cudaEventCreate(&t_k1[i]));
+      }
+  }
+  ~BatchStage() {
+    if (copy) cudaStreamDestroy(copy);
+    for (int b = 0; b < 2; b++) { if (copied[b]) cudaEventDestroy(copied[b]); if (consumed[b]) cudaEventDestroy(consumed[b]); }
+    if (t_c0[0])
+      for (int i = 0; i < BATCH_TIMED_STEPS; i++) {
+        cudaEventDestroy(t_c0[i]); cudaEventDestroy(t_c1[i]); cudaEventDestroy(t_k0[i]); cudaEventDestroy(t_k1[i]);
+      }
+  }
+};
+
 template <class T>
 struct TableHandle : HandleBase {
   BaseTable<T> table;
@@ -12,6 +54,7 @@ struct TableHandle : HandleBase {
   DevBuf<XYZZ<typename T::F>> d_result;  // one XYZZ result
   DevBuf<uint8_t> d_out;                 // RAW + COMP bytes
   DevBuf<int> d_err;
+  BatchStage batch;
   TableHandle() { kind = T::ID; }
 };
 
@@ -64,42 +107,57 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
   ZK_API_BEGIN
   auto* h = static_cast<TableHandle<T>*>(lookup_handle(handle, T::ID));
   ZK_REQUIRE(scalars && out && count > 0 && n > 0 && n <= h->table.n, ZK_EARG, "msm_batch: bad arguments");
+  for (size_t i = 0; i < count; i++) ZK_REQUIRE(scalars[i], ZK_EARG, "msm_batch: null scalar vector");
   cudaStream_t st = default_stream();
-  static thread_local cudaStream_t cs = nullptr;
-  if (!cs) ZK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-  DevBuf<uint32_t> d_sc[2];
-  d_sc[0].alloc(n * 8);
-  d_sc[1].alloc(n * 8);
-  DevBuf<uint8_t> d_outs(count * (T::RAW + T::COMP));
-  cudaEvent_t copied[2], consumed[2];
-  for (int b = 0; b < 2; b++) {
-    ZK_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-    ZK_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
-  }
+  BatchStage& B = h->batch;
+  B.ensure(n, count, T::RAW + T::COMP);
+  cudaStream_t cs = B.copy;
   ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st));
-  const bool was = h->table.pipelined;
-  h->table.set_pipelined(true);
+  PipelineScope<T> scope(h->table, cs);   // pipelined for the call; on unwind: drain both streams, drop the queue
+  B.steps_timed = 0;
   for (size_t i = 0; i < count; i++) {
-    int b = (int)(i & 1);
-    ZK_REQUIRE(scalars[i], ZK_EARG, "msm_batch: null scalar vector");
-    if (i >= 2) ZK_CUDA(cudaStreamWaitEvent(cs, consumed[b], 0));
-    ZK_CUDA(cudaMemcpyAsync(d_sc[b].p, scalars[i], n * 32, cudaMemcpyHostToDevice, cs));
-    ZK_CUDA(cudaEventRecord(copied[b], cs));
-    ZK_CUDA(cudaStreamWaitEvent(st, copied[b], 0));
-    k_check_scalars<<<cdiv(n, 256), 256, 0, st>>>(d_sc[b].p, (uint32_t)n, h->d_err.p);
-    h->table.run(d_sc[b].p, (uint32_t)n, nullptr, d_outs.p + i * (T::RAW + T::COMP), st);
-    ZK_CUDA(cudaEventRecord(consumed[b], st));
+    const int b = (int)(i & 1);
+    const bool tm = B.timed && i < (size_t)BATCH_TIMED_STEPS;
+    if (i >= 2) ZK_CUDA(cudaStreamWaitEvent(cs, B.consumed[b], 0));
+    if (tm) ZK_CUDA(cudaEventRecord(B.t_c0[i], cs));
+    ZK_CUDA(cudaMemcpyAsync(B.d_sc[b].p, scalars[i], n * 32, cudaMemcpyHostToDevice, cs));
+    if (tm) ZK_CUDA(cudaEventRecord(B.t_c1[i], cs));
+    ZK_CUDA(cudaEventRecord(B.copied[b], cs));
+    ZK_CUDA(cudaStreamWaitEvent(st, B.copied[b], 0));
+    if (tm) ZK_CUDA(cudaEventRecord(B.t_k0[i], st));
+    k_check_scalars<<<cdiv(n, 256), 256, 0, st>>>(B.d_sc[b].p, (uint32_t)n, h->d_err.p);
+    h->table.run(B.d_sc[b].p, (uint32_t)n, nullptr, B.d_outs.p + i * (T::RAW + T::COMP), st);
+    ZK_CUDA(cudaEventRecord(B.consumed[b], st));
+    if (tm) { ZK_CUDA(cudaEventRecord(B.t_k1[i], st)); B.steps_timed = (int)i + 1; }
   }
   h->table.join(st);
-  h->table.set_pipelined(was);
   int err = 0;
-  ZK_CUDA(cudaMemcpyAsync(out, d_outs.p, count * (T::RAW + T::COMP), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(out, B.d_outs.p, count * (T::RAW + T::COMP), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   ZK_CUDA(cudaStreamSynchronize(st));
   ZK_CUDA(cudaStreamSynchronize(cs));
-  for (int b = 0; b < 2; b++) { cudaEventDestroy(copied[b]); cudaEventDestroy(consumed[b]); }
   ZK_REQUIRE(err == 0, ZK_EPOINT, "msm_batch: scalar is not canonical (>= r)");
   ZK_API_END
+}
+
+// Per-step timing of the last zk_g*_table_msm_batch on this handle (enable before the call):
+// out[4 i + 0] = upload start, [1] = upload end, [2] = first kernel, [3] = last kernel of step i,
+// in ms since the first upload started.  Returns the number of steps written through *steps.
+template <class T>
+int api_table_batch_timing(TableHandle<T>* h, int enable, float* out, size_t cap, size_t* steps) {
+  BatchStage& B = h->batch;
+  if (out && steps) {
+    size_t k = std::min((size_t)B.steps_timed, cap / 4);
+    for (size_t i = 0; i < k; i++) {
+      ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 0], B.t_c0[0], B.t_c0[i]));
+      ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 1], B.t_c0[0], B.t_c1[i]));
+      ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 2], B.t_c0[0], B.t_k0[i]));
+      ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 3], B.t_c0[0], B.t_k1[i]));
+    }
+    *steps = k;
+  }
+  B.timed = enable != 0;
+  return ZK_OK;
 }
 
 template <class T>

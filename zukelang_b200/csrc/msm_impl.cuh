@@ -8,7 +8,7 @@
 #define ZK_BATCHED_AFFINE_DEFAULT 0
 #endif
 #ifndef ZK_ACC_VARIANT_DEFAULT
-#define ZK_ACC_VARIANT_DEFAULT 8
+#define ZK_ACC_VARIANT_DEFAULT 9
 #endif
 
 namespace zk {
@@ -102,19 +102,15 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   tile_sums.alloc(cdiv(nb, SCAN_TILE) + 1);
   entries.alloc((size_t)n * cfg.W);
   {
-    int per_sm = 0;
-    acc_variant = env_int(sizeof(F) > 48 ? "ZKB200_ACC_VARIANT_G2" : "ZKB200_ACC_VARIANT", sizeof(F) > 48 ? 4 : ZK_ACC_VARIANT_DEFAULT);
-    // 8 (G1 default): paired products, 254 registers, 2 blocks/SM; 1: plain mixed add at 128
-    // registers, 4 blocks/SM; 4 (G2 default): plain mixed add at 255 registers, 2 blocks/SM
-    if (acc_variant == 8 && sizeof(F) != sizeof(Fp)) acc_variant = 4;
-    if (acc_variant != 1 && acc_variant != 4 && acc_variant != 8) acc_variant = sizeof(F) > 48 ? 4 : 8;
-    switch (acc_variant) {
-      case 1: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 4, false>, 128, 0)); break;
-      case 4: ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false>, 128, 0)); break;
-      default:
-        if constexpr (sizeof(F) == sizeof(Fp))
-          ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_accumulate<F, 2, false, true>, 128, 0));
-    }
+    // 9 (G1 default): paired products + cp.async staging, 2 blocks/SM; 8: paired, direct loads;
+    // 5 (G2 default): plain mixed add + staging; 4: plain, direct loads, 2 blocks/SM; 1: plain at 128
+    // registers, 4 blocks/SM
+    constexpr bool is_g1 = sizeof(F) == sizeof(Fp);
+    acc_variant = env_int(is_g1 ? "ZKB200_ACC_VARIANT" : "ZKB200_ACC_VARIANT_G2", is_g1 ? ZK_ACC_VARIANT_DEFAULT : 5);
+    if (!is_g1 && acc_variant >= 8) acc_variant -= 4;
+    if (acc_variant != 1 && acc_variant != 4 && acc_variant != 5 && acc_variant != 8 && acc_variant != 9)
+      acc_variant = is_g1 ? ZK_ACC_VARIANT_DEFAULT : 5;
+    int per_sm = acc_occupancy();
     if (per_sm < 1) per_sm = 1;
     acc_blocks = (uint32_t)per_sm * (uint32_t)sm_count();
   }
@@ -202,13 +198,7 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   uint32_t grid = cdiv((uint64_t)count * cfg.W, 16 * 128);
   if (grid > acc_blocks) grid = acc_blocks;
   if (grid < 1) grid = 1;
-  switch (acc_variant) {
-    case 1: k_accumulate<F, 4, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
-    case 4: k_accumulate<F, 2, false><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb); break;
-    default:
-      if constexpr (sizeof(F) == sizeof(Fp))
-        k_accumulate<F, 2, false, true><<<grid, 128, 0, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, nb);
-  }
+  acc_launch(grid, bsum, st);
   ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));
   k_fix_partials<F><<<cdiv(nb, 128), 128, 0, st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p, heavy.p + 1);
   {
@@ -224,6 +214,38 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   queued++;
   ZK_CUDA(cudaGetLastError());
   if (!pipelined) join(st);
+}
+
+// the accumulation kernel selected by acc_variant: occupancy query and launch
+template <class T>
+template <class Fn>
+void BaseTable<T>::acc_dispatch(Fn&& fn) {
+  constexpr size_t SM = acc_stage_bytes<F>();
+  switch (acc_variant) {
+    case 1: fn(k_accumulate<F, 4, false, false>, (size_t)0); break;
+    case 4: fn(k_accumulate<F, 2, false, false>, (size_t)0); break;
+    case 5: fn(k_accumulate<F, 2, true, false>, SM); break;
+    case 8:
+      if constexpr (sizeof(F) == sizeof(Fp)) fn(k_accumulate<F, 2, false, true>, (size_t)0);
+      break;
+    default:
+      if constexpr (sizeof(F) == sizeof(Fp)) fn(k_accumulate<F, 2, true, true>, SM);
+  }
+}
+template <class T>
+int BaseTable<T>::acc_occupancy() {
+  int per_sm = 0;
+  acc_dispatch([&](auto kern, size_t smem) {
+    if (smem) ZK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ACC_THREADS, smem));
+  });
+  return per_sm;
+}
+template <class T>
+void BaseTable<T>::acc_launch(uint32_t grid, XYZZ<F>* bsum, cudaStream_t st) {
+  acc_dispatch([&](auto kern, size_t smem) {
+    kern<<<grid, ACC_THREADS, smem, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, cfg.nbuckets());
+  });
 }
 
 template <class T>

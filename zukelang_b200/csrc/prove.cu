@@ -151,9 +151,10 @@ static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* 
   uint32_t span = std::max(std::max(L.ti_cnt, L.h_cnt), std::max(L.mid_cnt, 1u));
   k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, vwy, Hq, k->d_sol.p, k->mid_index.p, k->d_rs.p, k->sA.p,
                                                       k->qB.scalars.p, k->qC.scalars.p);
-  // tails (bucket reduction, affine conversion) of A and C overlap the next accumulation
-  k->qC.table.set_pipelined(true);
-  k->qB.table.set_pipelined(true);
+  // tails (bucket reduction, affine conversion) of A and C overlap the next accumulation; an error
+  // between run() and join() drains the device and drops the queued tails (PipelineScope)
+  PipelineScope<G1Traits> scope1(k->qC.table);
+  PipelineScope<G2Traits> scope2(k->qB.table);
   k->qC.table.run(k->sA.p, 3 + L.ti_cnt, nullptr, k->d_out.p, st);                                           // A
   k->qC.table.run(k->qC.scalars.p, k->qC.table.n, nullptr, k->d_out.p + ZK_G1_OUT + ZK_G2_OUT, st);         // C
   k->qB.table.run(k->qB.scalars.p, k->qB.table.n, nullptr, k->d_out.p + ZK_G1_OUT, st);                     // B
@@ -424,8 +425,8 @@ int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* s
   uint8_t* o_waw = o;                      o += ZK_G2_OUT;
   uint8_t* o_yay = o;                      o += ZK_G1_OUT;
   uint8_t* o_bvwy = o;
-  k->q1.table.set_pipelined(true);
-  k->q2.table.set_pipelined(true);
+  PipelineScope<G1Traits> scope1(k->q1.table);
+  PipelineScope<G2Traits> scope2(k->q2.table);
   auto run1 = [&](int slot, uint8_t* out) { k->q1.table.run(at1(slot), k->cnt1[slot], nullptr, out, st, k->first1[slot]); };
   auto run2 = [&](int slot, uint8_t* out) { k->q2.table.run(at2(slot), k->cnt2[slot], nullptr, out, st, k->first2[slot]); };
   run1(0, o_vv); run1(1, o_yy); run1(5, o_h); run1(2, o_vav); run1(3, o_yay); run1(4, o_bvwy);

@@ -173,8 +173,21 @@ class Groth16Sparse:
                     ltgm={k: acc[k] * gminv % R for k in ios}, zt=zt, mids=mids, ios=ios)
 
     def keygen(self, rng: random.Random, circuit: SparseCircuit, w: Sequence[int]):
-        G1, G2 = self.C.G1, self.C.G2
+        """``keygen rng circuit qap`` of Protocol.S (protocol.mli:21) for a sparse circuit: returns
+        (pkey, vkey) only — the toxic waste is dropped, as groth16.ml:227-233 does."""
+        pkey, vkey, _ = self.keygen_with_trapdoor(rng, circuit, w)
+        return pkey, vkey
+
+    def keygen_with_trapdoor(self, rng: random.Random, circuit: SparseCircuit, w: Sequence[int]):
+        """TEST-ONLY variant that also returns (a, b, gm, d, t): whoever holds it can forge proofs.
+        The parity tests need it for the closed-form identities (SURVEY.md §8c iv)."""
         trapdoor = tuple(Fr.gen(rng) for _ in range(5))     # a, b, gm, d, t  (groth16.ml:51-55)
+        pkey, vkey = self.keygen_from_trapdoor(trapdoor, circuit, w)
+        return pkey, vkey, trapdoor
+
+    def keygen_from_trapdoor(self, trapdoor, circuit: SparseCircuit, w: Sequence[int]):
+        from .groth16 import VKey
+        G1, G2 = self.C.G1, self.C.G2
         a, b, gm, d, t = trapdoor
         sc = self.keygen_scalars(trapdoor, circuit, w)
         n = circuit.n
@@ -187,8 +200,15 @@ class Groth16Sparse:
         ltd = p1[o:o + len(sc["mids"])]; o += len(sc["mids"])
         pkey = DerivedPKey(a=p1[0], d1=p1[1], b1=p1[2], b2=p2[0], d2=p2[1], lag1=lag1, lag2=p2[3:], hk=hk,
                            ltd_mid=dict(zip(sc["mids"], ltd)))
-        vkey = dict(one1=G1.one, ltgm_io=dict(zip(sc["ios"], p1[o:])), one2=G2.one, gm=p2[2], d=p2[1])
-        return pkey, vkey, trapdoor
+        vkey = VKey(one1=G1.one, ltgm_io=dict(zip(sc["ios"], p1[o:])), one2=G2.one, gm=p2[2], d=p2[1],
+                    ab=self.C.Pairing.pairing(p1[0], p2[0]))               # groth16.ml:103
+        return pkey, vkey
+
+    def verify(self, w_io: Dict[Var, int], vkey, proof) -> bool:
+        """groth16.ml:163-173 — the verification key and equation do not depend on the basis the
+        prover worked in, so this is Groth16.Make(C).verify."""
+        from .groth16 import Make
+        return Make(self.C).verify(w_io, vkey, proof)
 
     def _key_handle(self, pkey: DerivedPKey, circuit: SparseCircuit) -> int:
         if self.shard in pkey._handles:
