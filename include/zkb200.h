@@ -45,8 +45,18 @@ extern "C" {
 #define ZK_G2_OUT 288
 
 /* ---- lifecycle -------------------------------------------------------------- */
-/* Select the CUDA device (-1 = keep the current one) and create the library stream. */
+/* Drive ONE CUDA device (-1 = keep the current one) and create the library stream. */
 int zk_init(int device);
+/* Drive ndev (1..8) devices of one box from this single process:
+ * devs[0] is the primary device (QAP / domain handles live there, results are combined there).
+ * Key and table handles loaded afterwards spread their base-point ranges over all the devices by
+ * themselves, and zk_groth16_prove* / zk_g*_table_msm* return FINISHED results: every device
+ * reduces its range on its own stream and stores its partial sum into the primary device's memory
+ * (peer-to-peer over NVLink; peer access between devs[0] and every other device is required,
+ * ZK_ECUDA otherwise), where the partials are added.  This is what lets the OCaml `prove`
+ * (protocol.mli:23) use the whole box.  The device list can only change after zk_shutdown. */
+int zk_init_devices(const int *devs, int ndev);
+int zk_device_count(void); /* devices driven; 0 before zk_init */
 int zk_shutdown(void);
 const char *zk_last_error(void);
 /* "name;sm_count;cc_major.cc_minor" */
@@ -80,11 +90,14 @@ int zk_g2_table_msm(uint64_t handle, const uint8_t *scalars, size_t n, uint8_t o
 int zk_g1_table_msm_batch(uint64_t handle, const uint8_t *const *scalars, size_t n, size_t count, uint8_t *out);
 int zk_g2_table_msm_batch(uint64_t handle, const uint8_t *const *scalars, size_t n, size_t count, uint8_t *out);
 /* Same with device-resident scalars / result, enqueued on `cuda_stream` (a cudaStream_t,
- * NULL = the library stream) without synchronising. */
+ * NULL = the library stream) without synchronising.  Device pointers belong to one device: these
+ * entry points (and zk_table_pipeline / zk_table_join) need a table that lives on ONE device
+ * (zk_init, or fewer than 4096 points per device), ZK_EARG otherwise. */
 int zk_g1_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *cuda_stream);
 int zk_g2_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *d_out, void *cuda_stream);
 /* info[0] = window bits c, [1] = windows W, [2] = bucket windows, [3] = buckets per window,
- * [4] = 1 (legacy field), [5] = device bytes, [6] = points, [7] = precomputed */
+ * [4] = 1 (legacy field), [5] = device bytes (all devices), [6] = points, [7] = precomputed;
+ * c / W are those of the primary device's part when the table is spread over several devices */
 int zk_table_info(uint64_t handle, uint64_t info[8]);
 /* Pipelining of consecutive *_msm_dev calls on one table.  Each MSM ends in a latency-bound
  * tail (bucket reduction, window combine, affine conversion: ~40 dependent point operations) whose
@@ -166,9 +179,11 @@ typedef struct {
 
 #define ZK_GROTH16_PROOF_OUT (ZK_G1_OUT + ZK_G2_OUT + ZK_G1_OUT) /* a | b | c point results */
 
-/* shard_index / shard_count: this process keeps slice shard_index of every list-valued field
- * (SURVEY.md section 8e); with shard_count > 1 zk_groth16_prove returns this shard's PARTIAL
- * sums, which the caller adds across shards (e.g. zk_g1_msm with unit scalars). */
+/* shard_index / shard_count = (0, 1): the whole key.  After zk_init_devices its list-valued fields
+ * are spread over the devices and zk_groth16_prove* still return the finished proof.
+ * shard_count > 1 (one PROCESS per GPU, e.g. torchrun): this process keeps slice shard_index of
+ * every list-valued field on its device and zk_groth16_prove* return this
+ * shard's PARTIAL sums, which the caller adds across shards (zk_g*_sum). */
 int zk_groth16_pk_load(const zk_groth16_pkey *pk, int shard_index, int shard_count, uint64_t *handle);
 /* Groth16.Make(C).prove (groth16.ml:235-237 then 123-161).  sol: m witness scalars; r, s: the two
  * Fr.gen draws of groth16.ml:124-125 (r first), supplied by the host RNG. */

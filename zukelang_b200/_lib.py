@@ -34,6 +34,8 @@ _u32p = POINTER(c_uint32)
 # name -> (restype, argtypes); mirrors include/zkb200.h one to one
 SIGNATURES = {
     "zk_init": (c_int, [c_int]),
+    "zk_init_devices": (c_int, [POINTER(c_int), c_int]),
+    "zk_device_count": (c_int, []),
     "zk_shutdown": (c_int, []),
     "zk_last_error": (c_char_p, []),
     "zk_device_info": (c_int, [c_char_p, c_size_t]),
@@ -136,13 +138,28 @@ def check(rc: int) -> None:
 
 
 def lib() -> ctypes.CDLL:
-    """The initialised library (selects the device of LOCAL_RANK, else device 0)."""
+    """The initialised library.  ZKB200_DEVICES="0,1,2,3" drives several devices from this one
+    process (zk_init_devices); otherwise the device of ZKB200_DEVICE / LOCAL_RANK, else device 0."""
     global _initialised
     l = load()
     if not _initialised:
-        dev = int(os.environ.get("ZKB200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-        check(l.zk_init(dev))
+        many = os.environ.get("ZKB200_DEVICES", "")
+        if many:
+            init_devices([int(x) for x in many.split(",")])
+        else:
+            dev = int(os.environ.get("ZKB200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            check(l.zk_init(dev))
         _initialised = True
+    return l
+
+
+def init_devices(devs) -> ctypes.CDLL:
+    """zk_init_devices: drive these CUDA devices from this process (devs[0] = primary)."""
+    global _initialised
+    l = load()
+    arr = (c_int * len(devs))(*devs)
+    check(l.zk_init_devices(arr, len(devs)))
+    _initialised = True
     return l
 
 

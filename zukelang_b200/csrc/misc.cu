@@ -253,15 +253,13 @@ int zk_table_profile(uint64_t handle, int enable, float stage_ms[4]) {
   using namespace zk;
   HandleBase* hb = lookup_handle(handle, 0);
   ZK_REQUIRE(hb->kind == 1 || hb->kind == 2, ZK_EARG, "table_profile: not a table handle");
-  if (hb->kind == 1) {
-    auto* h = static_cast<TableHandle<G1Traits>*>(hb);
-    if (stage_ms) h->table.stage_ms(stage_ms);
-    h->table.profile = enable != 0;
-  } else {
-    auto* h = static_cast<TableHandle<G2Traits>*>(hb);
-    if (stage_ms) h->table.stage_ms(stage_ms);
-    h->table.profile = enable != 0;
-  }
+  auto go = [&](auto* h) {          // stage times of the primary device's part
+    auto& t = h->parts[0]->table;
+    if (stage_ms) t.stage_ms(stage_ms);
+    for (auto& p : h->parts) p->table.profile = enable != 0;
+  };
+  if (hb->kind == 1) go(static_cast<TableHandle<G1Traits>*>(hb));
+  else go(static_cast<TableHandle<G2Traits>*>(hb));
   ZK_API_END
 }
 
@@ -281,15 +279,13 @@ int zk_table_pipeline(uint64_t handle, int enable) {
   using namespace zk;
   HandleBase* hb = lookup_handle(handle, 0);
   ZK_REQUIRE(hb->kind == 1 || hb->kind == 2, ZK_EARG, "table_pipeline: not a table handle");
-  if (hb->kind == 1) {
-    auto& t = static_cast<TableHandle<G1Traits>*>(hb)->table;
+  auto go = [&](auto* h) {
+    auto& t = h->single();
     if (!enable && t.queued) { ZK_CUDA(cudaDeviceSynchronize()); t.join(default_stream()); ZK_CUDA(cudaStreamSynchronize(default_stream())); }
     t.set_pipelined(enable != 0);
-  } else {
-    auto& t = static_cast<TableHandle<G2Traits>*>(hb)->table;
-    if (!enable && t.queued) { ZK_CUDA(cudaDeviceSynchronize()); t.join(default_stream()); ZK_CUDA(cudaStreamSynchronize(default_stream())); }
-    t.set_pipelined(enable != 0);
-  }
+  };
+  if (hb->kind == 1) go(static_cast<TableHandle<G1Traits>*>(hb));
+  else go(static_cast<TableHandle<G2Traits>*>(hb));
   ZK_API_END
 }
 
@@ -299,8 +295,8 @@ int zk_table_join(uint64_t handle, void* stream) {
   HandleBase* hb = lookup_handle(handle, 0);
   ZK_REQUIRE(hb->kind == 1 || hb->kind == 2, ZK_EARG, "table_join: not a table handle");
   cudaStream_t st = stream ? (cudaStream_t)stream : default_stream();
-  if (hb->kind == 1) static_cast<TableHandle<G1Traits>*>(hb)->table.join(st);
-  else static_cast<TableHandle<G2Traits>*>(hb)->table.join(st);
+  if (hb->kind == 1) static_cast<TableHandle<G1Traits>*>(hb)->single().join(st);
+  else static_cast<TableHandle<G2Traits>*>(hb)->single().join(st);
   ZK_API_END
 }
 
@@ -310,15 +306,14 @@ int zk_table_info(uint64_t handle, uint64_t info[8]) {
   HandleBase* hb = lookup_handle(handle, 0);
   ZK_REQUIRE(info && (hb->kind == 1 || hb->kind == 2), ZK_EARG, "table_info: not a table handle");
   MsmConfig cfg;
-  size_t bytes, n;
+  size_t bytes = 0, n;
   bool pre;
-  if (hb->kind == 1) {
-    auto* h = static_cast<TableHandle<G1Traits>*>(hb);
-    cfg = h->table.cfg; bytes = h->table.device_bytes(); n = h->table.n; pre = h->table.precomputed;
-  } else {
-    auto* h = static_cast<TableHandle<G2Traits>*>(hb);
-    cfg = h->table.cfg; bytes = h->table.device_bytes(); n = h->table.n; pre = h->table.precomputed;
-  }
+  auto go = [&](auto* h) {          // window shape of the primary part; bytes and points of the whole table
+    cfg = h->parts[0]->table.cfg; n = h->n; pre = h->parts[0]->table.precomputed;
+    for (auto& p : h->parts) bytes += p->table.device_bytes();
+  };
+  if (hb->kind == 1) go(static_cast<TableHandle<G1Traits>*>(hb));
+  else go(static_cast<TableHandle<G2Traits>*>(hb));
   info[0] = cfg.c; info[1] = cfg.W; info[2] = cfg.nwb; info[3] = cfg.B; info[4] = cfg.S;
   info[5] = bytes; info[6] = n; info[7] = pre;
   ZK_API_END

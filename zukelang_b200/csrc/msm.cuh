@@ -460,6 +460,23 @@ __global__ void k_finalize(const XYZZ<typename T::F>* __restrict__ results, int 
   T::serialize(a, out + (size_t)i * (T::RAW + T::COMP));
 }
 
+// Combine of the devices' partial sums: out[q] = sum_p gather[q * parts + p], as wire
+// bytes at out + q * out_stride; one block per q.  The parts stored their XYZZ partials into
+// `gather` on the primary device as peer-to-peer stores.
+template <class T>
+__global__ void k_sum_parts(const XYZZ<typename T::F>* __restrict__ gather, uint32_t parts, uint8_t* __restrict__ out,
+                            uint32_t out_stride) {
+  if (threadIdx.x) return;
+  const uint32_t q = blockIdx.x;
+  XYZZ<typename T::F> acc = load_vec_rw(&gather[(size_t)q * parts]);
+  for (uint32_t p = 1; p < parts; p++) {
+    XYZZ<typename T::F> x = load_vec_rw(&gather[(size_t)q * parts + p]);
+    acc.add(x);
+  }
+  Affine<typename T::F> a = acc.to_affine();
+  T::serialize(a, out + (size_t)q * out_stride);
+}
+
 // ---- table construction ---------------------------------------------------------
 // raw wire bytes -> Montgomery affine, curve check, identity flags
 template <class T>
@@ -586,21 +603,28 @@ struct BaseTable {
 };
 
 // Pipelines a table for the lifetime of the scope.  If the scope is left by an exception while
-// tails are still queued, the device is drained and the queue dropped, so that a later run() /
-// join() on the handle never writes through output pointers of the failed call.
+// tails are still queued, the table's device is drained and the queue dropped, so that a later
+// run() / join() on the handle never writes through output pointers of the failed call.
+int current_ctx();
+void set_ctx(int ctx);
 template <class T>
 struct PipelineScope {
   BaseTable<T>& t;
   bool was;
-  int exc;
+  int exc, ctx;
   cudaStream_t extra;
-  explicit PipelineScope(BaseTable<T>& t_, cudaStream_t extra_ = nullptr)
-      : t(t_), was(t_.pipelined), exc(std::uncaught_exceptions()), extra(extra_) { t.set_pipelined(true); }
+  PipelineScope(BaseTable<T>& t_, int ctx_, cudaStream_t extra_ = nullptr)
+      : t(t_), was(t_.pipelined), exc(std::uncaught_exceptions()), ctx(ctx_), extra(extra_) { t.set_pipelined(true); }
+  PipelineScope(const PipelineScope&) = delete;
+  PipelineScope& operator=(const PipelineScope&) = delete;
   ~PipelineScope() {
     if (std::uncaught_exceptions() > exc) {
+      const int keep = current_ctx();
+      try { set_ctx(ctx); } catch (...) {}
       cudaDeviceSynchronize();
       if (extra) cudaStreamSynchronize(extra);
       t.abort_queue();
+      try { set_ctx(keep); } catch (...) {}
     }
     t.pipelined = was;
   }

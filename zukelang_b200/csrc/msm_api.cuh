@@ -11,7 +11,6 @@ namespace zk {
 constexpr int BATCH_TIMED_STEPS = 64;
 struct BatchStage {
   DevBuf<uint32_t> d_sc[2];              // double-buffered scalar vectors
-  DevBuf<uint8_t> d_outs;                // count point results
   cudaStream_t copy = nullptr;           // upload stream
   cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
   // per-step timing (zk_table_batch_timing): upload start / end on the copy stream, first kernel /
@@ -20,10 +19,9 @@ struct BatchStage {
   int steps_timed = 0;
   cudaEvent_t t_c0[BATCH_TIMED_STEPS] = {}, t_c1[BATCH_TIMED_STEPS] = {}, t_k0[BATCH_TIMED_STEPS] = {},
               t_k1[BATCH_TIMED_STEPS] = {};
-  void ensure(size_t n, size_t count, size_t out_bytes) {
+  void ensure(size_t n) {
     d_sc[0].ensure(n * 8);
     d_sc[1].ensure(n * 8);
-    d_outs.ensure(count * out_bytes);
     if (!copy) {
       ZK_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
       for (int b = 0; b < 2; b++) {
@@ -47,19 +45,75 @@ struct BatchStage {
   }
 };
 
+// One device's share of a table: the base range [lo, lo + table.n).
 template <class T>
-struct TableHandle : HandleBase {
+struct TablePart {
+  int ctx = 0;
+  uint32_t lo = 0;
   BaseTable<T> table;
   DevBuf<uint32_t> d_scalars;            // staging for host-scalar calls
-  DevBuf<XYZZ<typename T::F>> d_result;  // one XYZZ result
-  DevBuf<uint8_t> d_out;                 // RAW + COMP bytes
-  DevBuf<int> d_err;
   BatchStage batch;
+  cudaEvent_t done = nullptr;            // this part's share of the current call is enqueued up to here
+  ~TablePart() { if (done) cudaEventDestroy(done); }
+};
+
+// A table handle: one part when the library drives one device or the caller shards across
+// processes itself, one part per device after zk_init_devices.  Partial sums of the parts are
+// stored into d_gather on the primary device (peer-to-peer stores) and added there.
+template <class T>
+struct TableHandle : HandleBase {
+  typedef typename T::F F;
+  uint32_t n = 0;
+  std::vector<std::unique_ptr<TablePart<T>>> parts;
+  DevBuf<XYZZ<F>> d_result;              // one XYZZ result (single part)
+  DevBuf<XYZZ<F>> d_gather;              // [slot][part]
+  DevBuf<uint8_t> d_out;                 // RAW + COMP bytes per slot
+  DevBuf<int> d_err;
+  cudaEvent_t ready = nullptr;           // primary stream: error flag cleared, parts may start
   TableHandle() { kind = T::ID; }
+  ~TableHandle() { if (ready) cudaEventDestroy(ready); }
+  BaseTable<T>& single() {
+    ZK_REQUIRE(parts.size() == 1, ZK_EARG, "this entry point takes device pointers: it needs a table on ONE device");
+    return parts[0]->table;
+  }
+  int active_parts(size_t count) const {   // parts that hold some of the first `count` points
+    int k = 0;
+    for (auto& p : parts) if (p->lo < count) k++;
+    return k;
+  }
 };
 
 // scalars must be canonical (< r): checked on the device for host-facing calls
 __global__ void k_check_scalars(const uint32_t* __restrict__ scalars, uint32_t n, int* __restrict__ err);
+
+template <class T>
+void table_alloc_common(TableHandle<T>* h) {
+  h->d_result.alloc(1);
+  h->d_out.alloc(T::RAW + T::COMP);
+  h->d_err.alloc(1);
+  ZK_CUDA(cudaEventCreateWithFlags(&h->ready, cudaEventDisableTiming));
+}
+
+// Splits [0, n) over `nparts` devices and loads every part on its own device.
+template <class T>
+void table_load_parts(TableHandle<T>* h, const uint8_t* bases, const uint8_t* inf_flags, uint32_t n, bool precompute,
+                      int window_bits, int nparts) {
+  h->n = n;
+  h->ctx = 0;
+  for (int p = 0; p < nparts; p++) {
+    uint32_t lo = (uint32_t)((uint64_t)n * p / nparts), hi = (uint32_t)((uint64_t)n * (p + 1) / nparts);
+    auto part = std::make_unique<TablePart<T>>();
+    part->ctx = p;
+    part->lo = lo;
+    CtxScope scope(p);
+    part->table.load(bases + (size_t)lo * T::RAW, inf_flags ? inf_flags + lo : nullptr, hi - lo, precompute, window_bits,
+                     stream_of(p));
+    ZK_CUDA(cudaEventCreateWithFlags(&part->done, cudaEventDisableTiming));
+    h->parts.push_back(std::move(part));
+  }
+  CtxScope scope(0);
+  table_alloc_common(h);
+}
 
 template <class T>
 int api_table_load(const uint8_t* bases, const uint8_t* inf_flags, size_t n, int precompute, int window_bits,
@@ -67,28 +121,55 @@ int api_table_load(const uint8_t* bases, const uint8_t* inf_flags, size_t n, int
   ZK_API_BEGIN
   ZK_REQUIRE(bases && handle && n > 0 && n < (1ull << 28), ZK_EARG, "table_load: bad arguments");
   auto h = std::make_unique<TableHandle<T>>();
-  h->table.load(bases, inf_flags, (uint32_t)n, precompute != 0, window_bits, default_stream());
-  h->d_result.alloc(1);
-  h->d_out.alloc(T::RAW + T::COMP);
-  h->d_err.alloc(1);
+  // small tables stay on the primary device: below ~2^12 points per device the fixed costs dominate
+  int nparts = device_count();
+  while (nparts > 1 && n / nparts < 4096) nparts--;
+  table_load_parts<T>(h.get(), bases, inf_flags, (uint32_t)n, precompute != 0, window_bits, nparts);
   *handle = register_handle(std::move(h));
   ZK_API_END
 }
 
+// One MSM with host scalars.  Several parts: every device uploads ITS slice of the scalars over its
+// own PCIe link, reduces its base range and stores the XYZZ partial sum into the primary device's
+// gather buffer; the primary device adds the partials and converts to wire bytes.
 template <class T>
 void table_msm_host(TableHandle<T>* h, const uint8_t* scalars, size_t n, uint8_t* out) {
-  cudaStream_t st = default_stream();
-  ZK_REQUIRE(scalars && out && n > 0 && n <= h->table.n, ZK_EARG, "msm: scalar count out of range");
-  h->d_scalars.ensure(n * 8);
-  ZK_CUDA(cudaMemcpyAsync(h->d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
-  ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st));
-  k_check_scalars<<<cdiv(n, 256), 256, 0, st>>>(h->d_scalars.p, (uint32_t)n, h->d_err.p);
-  h->table.run(h->d_scalars.p, (uint32_t)n, h->d_result.p, h->d_out.p, st);
-  h->table.join(st);
+  ZK_REQUIRE(scalars && out && n > 0 && n <= h->n, ZK_EARG, "msm: scalar count out of range");
+  CtxScope primary(0);
+  cudaStream_t st0 = stream_of(0);
+  ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st0));
+  const int active = h->active_parts(n);
+  if (h->parts.size() == 1) {
+    TablePart<T>& P = *h->parts[0];
+    P.d_scalars.ensure(n * 8);
+    ZK_CUDA(cudaMemcpyAsync(P.d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st0));
+    k_check_scalars<<<cdiv(n, 256), 256, 0, st0>>>(P.d_scalars.p, (uint32_t)n, h->d_err.p);
+    P.table.run(P.d_scalars.p, (uint32_t)n, h->d_result.p, h->d_out.p, st0);
+    P.table.join(st0);
+  } else {
+    h->d_gather.ensure(active);
+    ZK_CUDA(cudaEventRecord(h->ready, st0));
+    for (int p = 0; p < active; p++) {
+      TablePart<T>& P = *h->parts[p];
+      CtxScope scope(P.ctx);
+      cudaStream_t st = stream_of(P.ctx);
+      const uint32_t cnt = (uint32_t)std::min<size_t>(n, (size_t)P.lo + P.table.n) - P.lo;
+      P.d_scalars.ensure((size_t)cnt * 8);
+      ZK_CUDA(cudaStreamWaitEvent(st, h->ready, 0));
+      ZK_CUDA(cudaMemcpyAsync(P.d_scalars.p, scalars + (size_t)P.lo * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, st));
+      k_check_scalars<<<cdiv(cnt, 256), 256, 0, st>>>(P.d_scalars.p, cnt, h->d_err.p);
+      P.table.run(P.d_scalars.p, cnt, h->d_gather.p + p, nullptr, st);
+      P.table.join(st);
+      ZK_CUDA(cudaEventRecord(P.done, st));
+    }
+    for (int p = 0; p < active; p++) ZK_CUDA(cudaStreamWaitEvent(st0, h->parts[p]->done, 0));
+    k_sum_parts<T><<<1, 32, 0, st0>>>(h->d_gather.p, (uint32_t)active, h->d_out.p, T::RAW + T::COMP);
+    ZK_CUDA(cudaGetLastError());
+  }
   int err = 0;
-  ZK_CUDA(cudaMemcpyAsync(out, h->d_out.p, T::RAW + T::COMP, cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_CUDA(cudaMemcpyAsync(out, h->d_out.p, T::RAW + T::COMP, cudaMemcpyDeviceToHost, st0));
+  ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st0));
+  ZK_CUDA(cudaStreamSynchronize(st0));
   ZK_REQUIRE(err == 0, ZK_EPOINT, "msm: scalar is not canonical (>= r)");
 }
 
@@ -100,52 +181,84 @@ int api_table_msm(uint64_t handle, const uint8_t* scalars, size_t n, uint8_t* ou
   ZK_API_END
 }
 
-// `count` MSMs over the same table with host scalars: uploads are double-buffered on a copy
-// stream so that H2D of MSM i+1 overlaps the accumulation of MSM i, tails are batched.
+// `count` MSMs over the same table with host scalars: on every device the uploads are
+// double-buffered on a copy stream so that H2D of MSM i+1 overlaps the accumulation of MSM i, and
+// the tails are batched.
 template <class T>
 int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n, size_t count, uint8_t* out) {
   ZK_API_BEGIN
   auto* h = static_cast<TableHandle<T>*>(lookup_handle(handle, T::ID));
-  ZK_REQUIRE(scalars && out && count > 0 && n > 0 && n <= h->table.n, ZK_EARG, "msm_batch: bad arguments");
+  ZK_REQUIRE(scalars && out && count > 0 && count <= 65535 && n > 0 && n <= h->n, ZK_EARG, "msm_batch: bad arguments");
   for (size_t i = 0; i < count; i++) ZK_REQUIRE(scalars[i], ZK_EARG, "msm_batch: null scalar vector");
-  cudaStream_t st = default_stream();
-  BatchStage& B = h->batch;
-  B.ensure(n, count, T::RAW + T::COMP);
-  cudaStream_t cs = B.copy;
-  ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st));
-  PipelineScope<T> scope(h->table, cs);   // pipelined for the call; on unwind: drain both streams, drop the queue
-  B.steps_timed = 0;
+  constexpr size_t OUT = T::RAW + T::COMP;
+  CtxScope primary(0);
+  cudaStream_t st0 = stream_of(0);
+  const int active = h->active_parts(n);
+  const bool multi = h->parts.size() > 1;
+  h->d_out.ensure(count * OUT);
+  if (multi) h->d_gather.ensure(count * (size_t)active);
+  ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st0));
+  ZK_CUDA(cudaEventRecord(h->ready, st0));
+  // pipelined for the call; on unwind every device is drained and the queued tails are dropped
+  std::vector<std::unique_ptr<PipelineScope<T>>> scopes;
+  for (int p = 0; p < active; p++) {
+    TablePart<T>& P = *h->parts[p];
+    CtxScope scope(P.ctx);
+    const uint32_t cnt = (uint32_t)std::min<size_t>(n, (size_t)P.lo + P.table.n) - P.lo;
+    P.batch.ensure(cnt);
+    scopes.push_back(std::make_unique<PipelineScope<T>>(P.table, P.ctx, P.batch.copy));
+    P.batch.steps_timed = 0;
+    if (multi) ZK_CUDA(cudaStreamWaitEvent(stream_of(P.ctx), h->ready, 0));
+  }
   for (size_t i = 0; i < count; i++) {
     const int b = (int)(i & 1);
-    const bool tm = B.timed && i < (size_t)BATCH_TIMED_STEPS;
-    if (i >= 2) ZK_CUDA(cudaStreamWaitEvent(cs, B.consumed[b], 0));
-    if (tm) ZK_CUDA(cudaEventRecord(B.t_c0[i], cs));
-    ZK_CUDA(cudaMemcpyAsync(B.d_sc[b].p, scalars[i], n * 32, cudaMemcpyHostToDevice, cs));
-    if (tm) ZK_CUDA(cudaEventRecord(B.t_c1[i], cs));
-    ZK_CUDA(cudaEventRecord(B.copied[b], cs));
-    ZK_CUDA(cudaStreamWaitEvent(st, B.copied[b], 0));
-    if (tm) ZK_CUDA(cudaEventRecord(B.t_k0[i], st));
-    k_check_scalars<<<cdiv(n, 256), 256, 0, st>>>(B.d_sc[b].p, (uint32_t)n, h->d_err.p);
-    h->table.run(B.d_sc[b].p, (uint32_t)n, nullptr, B.d_outs.p + i * (T::RAW + T::COMP), st);
-    ZK_CUDA(cudaEventRecord(B.consumed[b], st));
-    if (tm) { ZK_CUDA(cudaEventRecord(B.t_k1[i], st)); B.steps_timed = (int)i + 1; }
+    for (int p = 0; p < active; p++) {     // the host thread interleaves the devices step by step
+      TablePart<T>& P = *h->parts[p];
+      BatchStage& B = P.batch;
+      CtxScope scope(P.ctx);
+      cudaStream_t st = stream_of(P.ctx), cs = B.copy;
+      const uint32_t cnt = (uint32_t)std::min<size_t>(n, (size_t)P.lo + P.table.n) - P.lo;
+      const bool tm = B.timed && i < (size_t)BATCH_TIMED_STEPS;
+      if (i >= 2) ZK_CUDA(cudaStreamWaitEvent(cs, B.consumed[b], 0));
+      if (tm) ZK_CUDA(cudaEventRecord(B.t_c0[i], cs));
+      ZK_CUDA(cudaMemcpyAsync(B.d_sc[b].p, scalars[i] + (size_t)P.lo * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, cs));
+      if (tm) ZK_CUDA(cudaEventRecord(B.t_c1[i], cs));
+      ZK_CUDA(cudaEventRecord(B.copied[b], cs));
+      ZK_CUDA(cudaStreamWaitEvent(st, B.copied[b], 0));
+      if (tm) ZK_CUDA(cudaEventRecord(B.t_k0[i], st));
+      k_check_scalars<<<cdiv(cnt, 256), 256, 0, st>>>(B.d_sc[b].p, cnt, h->d_err.p);
+      if (multi) P.table.run(B.d_sc[b].p, cnt, h->d_gather.p + i * active + p, nullptr, st);
+      else P.table.run(B.d_sc[b].p, cnt, nullptr, h->d_out.p + i * OUT, st);
+      ZK_CUDA(cudaEventRecord(B.consumed[b], st));
+      if (tm) { ZK_CUDA(cudaEventRecord(B.t_k1[i], st)); B.steps_timed = (int)i + 1; }
+    }
   }
-  h->table.join(st);
+  for (int p = 0; p < active; p++) {
+    TablePart<T>& P = *h->parts[p];
+    CtxScope scope(P.ctx);
+    P.table.join(stream_of(P.ctx));
+    if (multi) ZK_CUDA(cudaEventRecord(P.done, stream_of(P.ctx)));
+  }
+  if (multi) {
+    for (int p = 0; p < active; p++) ZK_CUDA(cudaStreamWaitEvent(st0, h->parts[p]->done, 0));
+    k_sum_parts<T><<<(unsigned)count, 32, 0, st0>>>(h->d_gather.p, (uint32_t)active, h->d_out.p, T::RAW + T::COMP);
+    ZK_CUDA(cudaGetLastError());
+  }
   int err = 0;
-  ZK_CUDA(cudaMemcpyAsync(out, B.d_outs.p, count * (T::RAW + T::COMP), cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaStreamSynchronize(st));
-  ZK_CUDA(cudaStreamSynchronize(cs));
+  ZK_CUDA(cudaMemcpyAsync(out, h->d_out.p, count * OUT, cudaMemcpyDeviceToHost, st0));
+  ZK_CUDA(cudaMemcpyAsync(&err, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st0));
+  ZK_CUDA(cudaStreamSynchronize(st0));
+  for (int p = 0; p < active; p++) ZK_CUDA(cudaStreamSynchronize(h->parts[p]->batch.copy));
   ZK_REQUIRE(err == 0, ZK_EPOINT, "msm_batch: scalar is not canonical (>= r)");
   ZK_API_END
 }
 
 // Per-step timing of the last zk_g*_table_msm_batch on this handle (enable before the call):
 // out[4 i + 0] = upload start, [1] = upload end, [2] = first kernel, [3] = last kernel of step i,
-// in ms since the first upload started.  Returns the number of steps written through *steps.
+// in ms since the first upload started (first device's part).  *steps = steps written.
 template <class T>
 int api_table_batch_timing(TableHandle<T>* h, int enable, float* out, size_t cap, size_t* steps) {
-  BatchStage& B = h->batch;
+  BatchStage& B = h->parts[0]->batch;
   if (out && steps) {
     size_t k = std::min((size_t)B.steps_timed, cap / 4);
     for (size_t i = 0; i < k; i++) {
@@ -156,7 +269,7 @@ int api_table_batch_timing(TableHandle<T>* h, int enable, float* out, size_t cap
     }
     *steps = k;
   }
-  B.timed = enable != 0;
+  for (auto& p : h->parts) p->batch.timed = enable != 0;
   return ZK_OK;
 }
 
@@ -164,9 +277,9 @@ template <class T>
 int api_table_msm_dev(uint64_t handle, const void* d_scalars, size_t n, void* d_out, void* stream) {
   ZK_API_BEGIN
   auto* h = static_cast<TableHandle<T>*>(lookup_handle(handle, T::ID));
-  ZK_REQUIRE(d_scalars && d_out && n > 0 && n <= h->table.n, ZK_EARG, "msm_dev: bad arguments");
+  ZK_REQUIRE(d_scalars && d_out && n > 0 && n <= h->n, ZK_EARG, "msm_dev: bad arguments");
   cudaStream_t st = stream ? (cudaStream_t)stream : default_stream();
-  h->table.run((const uint32_t*)d_scalars, (uint32_t)n, nullptr, (uint8_t*)d_out, st);
+  h->single().run((const uint32_t*)d_scalars, (uint32_t)n, nullptr, (uint8_t*)d_out, st);
   ZK_API_END
 }
 
@@ -181,11 +294,8 @@ int api_msm_oneshot(const uint8_t* bases, const uint8_t* inf_flags, const uint8_
     return ZK_OK;
   }
   ZK_REQUIRE(bases && scalars && n < (1ull << 28), ZK_EARG, "msm: bad arguments");
-  TableHandle<T> h;
-  h.table.load(bases, inf_flags, (uint32_t)n, false, 0, default_stream());
-  h.d_result.alloc(1);
-  h.d_out.alloc(T::RAW + T::COMP);
-  h.d_err.alloc(1);
+  TableHandle<T> h;     // one-shot: bases are parsed and uploaded for this call only, on the primary device
+  table_load_parts<T>(&h, bases, inf_flags, (uint32_t)n, false, 0, 1);
   table_msm_host<T>(&h, scalars, n, out);
   ZK_API_END
 }

@@ -58,18 +58,35 @@ struct G16Layout {
   int singles;  // 1 on the shard that owns a, b1, d1, b2, d2
 };
 
-struct Groth16Key : HandleBase {
+// One device's share of the key: slice [len * i / cnt, len * (i + 1) / cnt) of every list-valued field.
+struct Groth16Part {
+  int ctx = 0;
   G16Layout lay;
-  uint32_t m = 0, n_mid = 0;
   Query<G1Traits> qC;       // [a, b1, d1 | ti1 | tiztd | ltd_mid]; A uses the prefix 3 + ti_cnt
   Query<G2Traits> qB;       // [b2, d2 | ti2]
   DevBuf<uint32_t> sA;      // scalars of A (prefix of the qC table)
   DevBuf<uint32_t> mid_index;
+  DevBuf<XYZZ<Fp>> r1;      // scratch results when this is the only part
+  DevBuf<XYZZ<Fp2>> r2;
+  cudaEvent_t done = nullptr;
+  ~Groth16Part() { if (done) cudaEventDestroy(done); }
+};
+
+// Proving-key handle.  One part: the whole key on one device, or shard (i, N) of a key sharded
+// across PROCESSES by the caller (prove then returns that shard's partial sums).  Several parts:
+// after zk_init_devices the key's base ranges are spread over the devices of this process and
+// prove returns the finished proof — the parts read their scalars from the primary device and
+// store their partial sums into g1 / g2 there (peer-to-peer over NVLink).
+struct Groth16Key : HandleBase {
+  uint32_t n = 0, m = 0, n_mid = 0;
+  std::vector<std::unique_ptr<Groth16Part>> parts;
   DevBuf<uint32_t> d_sol, d_rs;
-  DevBuf<XYZZ<Fp>> r1;      // A, C
-  DevBuf<XYZZ<Fp2>> r2;     // B
+  DevBuf<XYZZ<Fp>> g1;      // [A, C][part]
+  DevBuf<XYZZ<Fp2>> g2;     // [part]
   DevBuf<uint8_t> d_out;
+  cudaEvent_t ready = nullptr;
   Groth16Key() { kind = 4; }
+  ~Groth16Key() { if (ready) cudaEventDestroy(ready); }
 };
 
 static __global__ void __launch_bounds__(128)
@@ -113,60 +130,98 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
                  (pk->n_mid == 0 || (pk->ltd_mid && pk->mid_index)),
              ZK_EARG, "groth16_pk_load: null key field");
   for (size_t j = 0; j < pk->n_mid; j++) ZK_REQUIRE(pk->mid_index[j] < pk->m, ZK_EARG, "groth16_pk_load: mid_index out of range");
-  cudaStream_t st = default_stream();
   auto k = std::make_unique<Groth16Key>();
-  G16Layout& L = k->lay;
-  L.n = (uint32_t)pk->n;
+  k->n = (uint32_t)pk->n;
   k->m = (uint32_t)pk->m;
   k->n_mid = (uint32_t)pk->n_mid;
-  slice(pk->n, shard_index, shard_count, &L.ti_lo, &L.ti_cnt);
-  slice(pk->n_h ? pk->n_h : pk->n - 1, shard_index, shard_count, &L.h_lo, &L.h_cnt);
-  slice(pk->n_mid, shard_index, shard_count, &L.mid_lo, &L.mid_cnt);
-  L.singles = shard_index == 0;
-  std::vector<uint8_t> t1, t2;
-  append(t1, pk->a, 96); append(t1, pk->b1, 96); append(t1, pk->d1, 96);
-  append(t1, pk->ti1 + (size_t)L.ti_lo * 96, (size_t)L.ti_cnt * 96);
-  append(t1, pk->tiztd + (size_t)L.h_lo * 96, (size_t)L.h_cnt * 96);
-  if (L.mid_cnt) append(t1, pk->ltd_mid + (size_t)L.mid_lo * 96, (size_t)L.mid_cnt * 96);
-  append(t2, pk->b2, 192); append(t2, pk->d2, 192);
-  append(t2, pk->ti2 + (size_t)L.ti_lo * 192, (size_t)L.ti_cnt * 192);
-  k->qC.load(t1, 3 + L.ti_cnt + L.h_cnt + L.mid_cnt, st);
-  k->qB.load(t2, 2 + L.ti_cnt, st);
-  k->sA.alloc((size_t)(3 + L.ti_cnt) * 8);
-  k->mid_index.alloc(pk->n_mid ? pk->n_mid : 1);
-  if (pk->n_mid) ZK_CUDA(cudaMemcpyAsync(k->mid_index.p, pk->mid_index, pk->n_mid * 4, cudaMemcpyHostToDevice, st));
+  // a key given whole to a process that drives several devices is spread over them; a key the
+  // caller shards itself (shard_count > 1: one process per GPU) stays on this process' device
+  int nparts = shard_count == 1 ? device_count() : 1;
+  while (nparts > 1 && pk->n / nparts < 4096) nparts--;
+  for (int p = 0; p < nparts; p++) {
+    const int idx = shard_count == 1 ? p : shard_index, cnt = shard_count == 1 ? nparts : shard_count;
+    auto part = std::make_unique<Groth16Part>();
+    part->ctx = p;
+    CtxScope scope(p);
+    cudaStream_t st = stream_of(p);
+    G16Layout& L = part->lay;
+    L.n = (uint32_t)pk->n;
+    slice(pk->n, idx, cnt, &L.ti_lo, &L.ti_cnt);
+    slice(pk->n_h ? pk->n_h : pk->n - 1, idx, cnt, &L.h_lo, &L.h_cnt);
+    slice(pk->n_mid, idx, cnt, &L.mid_lo, &L.mid_cnt);
+    L.singles = idx == 0;
+    std::vector<uint8_t> t1, t2;
+    append(t1, pk->a, 96); append(t1, pk->b1, 96); append(t1, pk->d1, 96);
+    append(t1, pk->ti1 + (size_t)L.ti_lo * 96, (size_t)L.ti_cnt * 96);
+    append(t1, pk->tiztd + (size_t)L.h_lo * 96, (size_t)L.h_cnt * 96);
+    if (L.mid_cnt) append(t1, pk->ltd_mid + (size_t)L.mid_lo * 96, (size_t)L.mid_cnt * 96);
+    append(t2, pk->b2, 192); append(t2, pk->d2, 192);
+    append(t2, pk->ti2 + (size_t)L.ti_lo * 192, (size_t)L.ti_cnt * 192);
+    part->qC.load(t1, 3 + L.ti_cnt + L.h_cnt + L.mid_cnt, st);
+    part->qB.load(t2, 2 + L.ti_cnt, st);
+    part->sA.alloc((size_t)(3 + L.ti_cnt) * 8);
+    part->mid_index.alloc(pk->n_mid ? pk->n_mid : 1);
+    if (pk->n_mid) ZK_CUDA(cudaMemcpyAsync(part->mid_index.p, pk->mid_index, pk->n_mid * 4, cudaMemcpyHostToDevice, st));
+    part->r1.alloc(2);
+    part->r2.alloc(1);
+    ZK_CUDA(cudaEventCreateWithFlags(&part->done, cudaEventDisableTiming));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    k->parts.push_back(std::move(part));
+  }
+  CtxScope primary(0);
   k->d_sol.alloc((size_t)pk->m * 8);
   k->d_rs.alloc(16);
-  k->r1.alloc(2);
-  k->r2.alloc(1);
+  k->g1.alloc(2 * (size_t)nparts);
+  k->g2.alloc(nparts);
   k->d_out.alloc(ZK_GROTH16_PROOF_OUT);
-  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_CUDA(cudaEventCreateWithFlags(&k->ready, cudaEventDisableTiming));
   *handle = register_handle(std::move(k));
   ZK_API_END
 }
 
-static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* flag, cudaStream_t st, uint8_t* proof_out) {
+// vwy, Hq, flag: on the primary device, ready in stream order on st0.
+static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* flag, cudaStream_t st0, uint8_t* proof_out) {
   using namespace zk;
-  const G16Layout& L = k->lay;
-  uint32_t span = std::max(std::max(L.ti_cnt, L.h_cnt), std::max(L.mid_cnt, 1u));
-  k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, vwy, Hq, k->d_sol.p, k->mid_index.p, k->d_rs.p, k->sA.p,
-                                                      k->qB.scalars.p, k->qC.scalars.p);
-  // tails (bucket reduction, affine conversion) of A and C overlap the next accumulation; an error
-  // between run() and join() drains the device and drops the queued tails (PipelineScope)
-  PipelineScope<G1Traits> scope1(k->qC.table);
-  PipelineScope<G2Traits> scope2(k->qB.table);
-  k->qC.table.run(k->sA.p, 3 + L.ti_cnt, nullptr, k->d_out.p, st);                                           // A
-  k->qC.table.run(k->qC.scalars.p, k->qC.table.n, nullptr, k->d_out.p + ZK_G1_OUT + ZK_G2_OUT, st);         // C
-  k->qB.table.run(k->qB.scalars.p, k->qB.table.n, nullptr, k->d_out.p + ZK_G1_OUT, st);                     // B
-  // all three accumulations are enqueued; the G2 tail runs on the auxiliary stream next to the G1 tail
-  cudaStream_t aux = fork_aux(st);
-  k->qB.table.join(aux);
-  k->qC.table.join(st);
-  join_aux(st);
+  const int np = (int)k->parts.size();
+  if (np > 1) ZK_CUDA(cudaEventRecord(k->ready, st0));
+  for (int p = 0; p < np; p++) {
+    Groth16Part& P = *k->parts[p];
+    const G16Layout& L = P.lay;
+    CtxScope scope(P.ctx);
+    cudaStream_t st = stream_of(P.ctx);
+    if (P.ctx != 0) ZK_CUDA(cudaStreamWaitEvent(st, k->ready, 0));
+    uint32_t span = std::max(std::max(L.ti_cnt, L.h_cnt), std::max(L.mid_cnt, 1u));
+    // the scalars of this part's three MSMs, read from the primary device's V | W, h and witness
+    k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, vwy, Hq, k->d_sol.p, P.mid_index.p, k->d_rs.p, P.sA.p,
+                                                        P.qB.scalars.p, P.qC.scalars.p);
+    // tails (bucket reduction, affine conversion) of A and C overlap the next accumulation; an error
+    // between run() and join() drains the device and drops the queued tails (PipelineScope)
+    PipelineScope<G1Traits> scope1(P.qC.table, P.ctx);
+    PipelineScope<G2Traits> scope2(P.qB.table, P.ctx);
+    XYZZ<Fp>* rA = np > 1 ? k->g1.p + p : P.r1.p;
+    XYZZ<Fp>* rC = np > 1 ? k->g1.p + np + p : P.r1.p + 1;
+    XYZZ<Fp2>* rB = np > 1 ? k->g2.p + p : P.r2.p;
+    uint8_t* o = np > 1 ? nullptr : k->d_out.p;       // one part: wire bytes straight from the tail
+    P.qC.table.run(P.sA.p, 3 + L.ti_cnt, rA, o, st);                                                       // A
+    P.qC.table.run(P.qC.scalars.p, P.qC.table.n, rC, o ? o + ZK_G1_OUT + ZK_G2_OUT : nullptr, st);         // C
+    P.qB.table.run(P.qB.scalars.p, P.qB.table.n, rB, o ? o + ZK_G1_OUT : nullptr, st);                     // B
+    // all three accumulations are enqueued; the G2 tail runs on the auxiliary stream next to the G1 tail
+    cudaStream_t aux = fork_aux(st);
+    P.qB.table.join(aux);
+    P.qC.table.join(st);
+    join_aux(st);
+    if (np > 1) ZK_CUDA(cudaEventRecord(P.done, st));
+  }
+  if (np > 1) {
+    for (int p = 0; p < np; p++) ZK_CUDA(cudaStreamWaitEvent(st0, k->parts[p]->done, 0));
+    k_sum_parts<G1Traits><<<2, 32, 0, st0>>>(k->g1.p, (uint32_t)np, k->d_out.p, ZK_G1_OUT + ZK_G2_OUT);   // A, C
+    k_sum_parts<G2Traits><<<1, 32, 0, st0>>>(k->g2.p, (uint32_t)np, k->d_out.p + ZK_G1_OUT, ZK_G2_OUT);   // B
+    ZK_CUDA(cudaGetLastError());
+  }
   int fl[2];
-  ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_GROTH16_PROOF_OUT, cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaMemcpyAsync(fl, flag, sizeof(fl), cudaMemcpyDeviceToHost, st));
-  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_GROTH16_PROOF_OUT, cudaMemcpyDeviceToHost, st0));
+  ZK_CUDA(cudaMemcpyAsync(fl, flag, sizeof(fl), cudaMemcpyDeviceToHost, st0));
+  ZK_CUDA(cudaStreamSynchronize(st0));
   ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "groth16_prove: scalar is not canonical (>= r)");
   ZK_REQUIRE(fl[1] == 0, ZK_EREMAINDER, "groth16_prove: V*W - Y is not divisible by the target (QAP.ml:134)");
 }
@@ -192,7 +247,7 @@ int zk_groth16_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* sol
   auto* qh = static_cast<QapHandle*>(lookup_handle(qap_handle, 3));
   QapDevice& q = qh->q;
   ZK_REQUIRE(sol && r && s && proof_out, ZK_EARG, "groth16_prove: null argument");
-  ZK_REQUIRE(q.n == k->lay.n && q.m == k->m, ZK_EARG, "groth16_prove: key and QAP dimensions differ");
+  ZK_REQUIRE(q.n == k->n && q.m == k->m, ZK_EARG, "groth16_prove: key and QAP dimensions differ");
   check_rs(r, s);
   cudaStream_t st = default_stream();
   ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
@@ -213,7 +268,7 @@ int zk_groth16_prove_coeffs(uint64_t pk_handle, uint64_t qap_handle, const uint8
   auto* qh = static_cast<QapHandle*>(lookup_handle(qap_handle, 3));
   QapDevice& q = qh->q;
   ZK_REQUIRE(vwy && sol && r && s && proof_out, ZK_EARG, "groth16_prove_coeffs: null argument");
-  ZK_REQUIRE(q.n == k->lay.n, ZK_EARG, "groth16_prove_coeffs: key and domain dimensions differ");
+  ZK_REQUIRE(q.n == k->n, ZK_EARG, "groth16_prove_coeffs: key and domain dimensions differ");
   check_rs(r, s);
   cudaStream_t st = default_stream();
   qh->d_raw.ensure(3 * (size_t)q.n * 8);
@@ -238,7 +293,7 @@ int zk_groth16_prove_r1cs(uint64_t pk_handle, uint64_t domain_handle, const uint
   auto* dh = static_cast<EvalDomainHandle*>(lookup_handle(domain_handle, 6));
   EvalDomain& d = dh->d;
   ZK_REQUIRE(sol && r && s && proof_out, ZK_EARG, "groth16_prove_r1cs: null argument");
-  ZK_REQUIRE(d.n == k->lay.n && d.m == k->m, ZK_EARG, "groth16_prove_r1cs: key and domain dimensions differ");
+  ZK_REQUIRE(d.n == k->n && d.m == k->m, ZK_EARG, "groth16_prove_r1cs: key and domain dimensions differ");
   check_rs(r, s);
   cudaStream_t st = default_stream();
   ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
@@ -251,9 +306,9 @@ int zk_groth16_prove_r1cs(uint64_t pk_handle, uint64_t domain_handle, const uint
 
 int zk_key_free(uint64_t handle) {
   ZK_API_BEGIN
-  ZK_CUDA(cudaDeviceSynchronize());
   zk::HandleBase* h = zk::lookup_handle(handle, 0);
   ZK_REQUIRE(h->kind == 4 || h->kind == 5, ZK_EARG, "key_free: not a key handle");
+  zk::sync_all_devices();
   zk::drop_handle(handle);
   ZK_API_END
 }
@@ -425,8 +480,8 @@ int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* s
   uint8_t* o_waw = o;                      o += ZK_G2_OUT;
   uint8_t* o_yay = o;                      o += ZK_G1_OUT;
   uint8_t* o_bvwy = o;
-  PipelineScope<G1Traits> scope1(k->q1.table);
-  PipelineScope<G2Traits> scope2(k->q2.table);
+  PipelineScope<G1Traits> scope1(k->q1.table, k->ctx);
+  PipelineScope<G2Traits> scope2(k->q2.table, k->ctx);
   auto run1 = [&](int slot, uint8_t* out) { k->q1.table.run(at1(slot), k->cnt1[slot], nullptr, out, st, k->first1[slot]); };
   auto run2 = [&](int slot, uint8_t* out) { k->q2.table.run(at2(slot), k->cnt2[slot], nullptr, out, st, k->first2[slot]); };
   run1(0, o_vv); run1(1, o_yy); run1(5, o_h); run1(2, o_vav); run1(3, o_yay); run1(4, o_bvwy);
