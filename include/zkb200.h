@@ -122,7 +122,9 @@ int zk_table_free(uint64_t handle);
 
 /* ---- sum of k points (combining the shards' partial results) ------
  * points: k uncompressed points; out: a point result.  Replaces G.sum / repeated G.( + )
- * (curve.ml:163,178).  The _dev form takes device pointers and enqueues on cuda_stream. */
+ * (curve.ml:163,178).  The _dev forms take device pointers and enqueue on cuda_stream; being
+ * asynchronous they cannot return ZK_EPOINT: an input point that does not parse makes them write
+ * 0xff into every byte of the affected result, which no parser of this library accepts. */
 int zk_g1_sum(const uint8_t *points, size_t k, uint8_t out[ZK_G1_OUT]);
 int zk_g2_sum(const uint8_t *points, size_t k, uint8_t out[ZK_G2_OUT]);
 int zk_g1_sum_dev(const void *d_points, size_t k, void *d_out, void *cuda_stream);

@@ -1,5 +1,5 @@
 // Host simulation of the experimental FP64-pipe Montgomery product (csrc/exp/mont_f64.cuh).
-#include "../../zukelang_b200/csrc/exp/mont_f64.cuh"
+#include "../../tools/exp/mont_f64.cuh"
 
 extern "C" void sim_f64_mul(const uint64_t* a, const uint64_t* b, const uint64_t* p, uint64_t n0inv, uint64_t* out) {
   f64mont::Limbs A, B, P;

@@ -246,7 +246,7 @@ def test_square_roots_and_subgroup_check(simp):
     assert simp.sim_in_subgroup(0, (ctypes.c_uint32 * 24)(*_enc_aff(G1, (x, y), 12))) == 0
 
 
-# ---- experimental FP64-pipe Montgomery product (csrc/exp/mont_f64.cuh; round-2 candidate) --------
+# ---- experimental FP64-pipe Montgomery product (tools/exp/mont_f64.cuh; round-2 candidate) --------
 def test_f64_limb_product_montgomery():
     out = tempfile.mkdtemp(prefix="zk_host_sim_")
     so = os.path.join(out, "sim_f64.so")

@@ -1,5 +1,5 @@
 // Round-2 experiment: throughput of the Fp Montgomery product with limb
-// products on the FP64 pipe (csrc/exp/mont_f64.cuh) against the shipped IMAD.WIDE product
+// products on the FP64 pipe (tools/exp/mont_f64.cuh) against the shipped IMAD.WIDE product
 // (csrc/mont.cuh), register resident, with a bit-exact cross-check of the two.  Standalone.
 //
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr \
@@ -7,7 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include "ec.cuh"
-#include "exp/mont_f64.cuh"
+#include "mont_f64.cuh"
 
 using f64mont::Limbs;
 

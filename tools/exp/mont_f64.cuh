@@ -22,7 +22,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
-#include "../ptx.cuh"
+#include "../../zukelang_b200/csrc/ptx.cuh"
 
 namespace f64mont {
 

@@ -21,7 +21,6 @@
 // A BaseTable built with `precompute` holds 2^(c*w) * P_i for every window w, so all windows
 // share ONE set of 2^(c-1) buckets: the bucket reduction shrinks W times and the window combine
 // disappears, at the price of W times the table bytes — cheap against 180 GB of HBM3e.
-// (msm_ba.cuh holds an experimental batched-affine accumulation, off by default.)
 #pragma once
 #include <exception>
 #include "common.cuh"
@@ -64,14 +63,21 @@ __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* k, int pos, int 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
 k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip, uint32_t n, uint32_t first,
-         uint32_t stride, MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries) {
+         uint32_t stride, MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries,
+         int* __restrict__ err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (skip && skip[first + i]) return;
   uint32_t k[8];
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * (size_t)i);
   uint4 a = __ldg(sp), b = __ldg(sp + 1);
   k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+  if (!SCATTER && err) {   // host-facing calls: a scalar >= r is an error (ZK_EPOINT), never reduced silently
+    uint32_t m[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) m[j] = FrParams::mod(j);
+    if (Fr::geq_raw(k, m)) { atomicExch(err, 1); return; }
+  }
+  if (skip && skip[first + i]) return;
   if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) return;
   uint32_t flip = 0;
   {
@@ -103,7 +109,8 @@ k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip,
   }
 }
 
-// Step 2: three-kernel exclusive scan (2048 elements per block).
+// Step 2: two-kernel exclusive scan (2048 elements per block): tile sums, then every block adds up
+// the sums of the tiles before it (at most a few hundred values) and scans its own tile.
 constexpr int SCAN_THREADS = 512, SCAN_ITEMS = 4, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums) {
@@ -143,34 +150,28 @@ k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restri
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of tile sums in place (any count, carried tile by tile)
-static __global__ void __launch_bounds__(1024)
-k_scan_spine(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
-  __shared__ uint32_t ws[32];
-  __shared__ uint32_t total;
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < ntiles ? tile_sums[i] : 0;
-    uint32_t ex = block_exclusive_scan(v, &total, ws);
-    if (i < ntiles) tile_sums[i] = ex + carry;
-    carry += total;
-    __syncthreads();
-  }
-}
-
-// writes offsets[0..n] (exclusive scan, offsets[n] = grand total) and a copy in cursor[0..n)
+// writes offsets[0..n] (exclusive scan, offsets[n] = grand total) and a copy in cursor[0..n);
+// clears `in` (the bucket histogram) behind itself, so that the next MSM on the table finds it zeroed
 static __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ tile_sums,
+k_scan_apply(uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ tile_sums,
              uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
   __shared__ uint32_t ws[32];
   __shared__ uint32_t total;
+  uint32_t before = 0;
+  for (uint32_t i = threadIdx.x; i < blockIdx.x; i += blockDim.x) before += tile_sums[i];
+  block_exclusive_scan(before, &total, ws);
+  const uint32_t tile_base = total;
+  __syncthreads();
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
   uint32_t s = 0;
 #pragma unroll
-  for (int j = 0; j < SCAN_ITEMS; j++) { v[j] = (base + j < n) ? in[base + j] : 0; s += v[j]; }
-  uint32_t ex = block_exclusive_scan(s, &total, ws) + tile_sums[blockIdx.x];
+  for (int j = 0; j < SCAN_ITEMS; j++) {
+    v[j] = (base + j < n) ? in[base + j] : 0;
+    if (base + j < n) in[base + j] = 0;
+    s += v[j];
+  }
+  uint32_t ex = block_exclusive_scan(s, &total, ws) + tile_base;
 #pragma unroll
   for (int j = 0; j < SCAN_ITEMS; j++) {
     if (base + j < n) { offsets[base + j] = ex; cursor[base + j] = ex; }
@@ -289,24 +290,38 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
   else store_vec(&partial[2 * (size_t)t + (e0 >= offsets[b] ? 0 : 1)], acc);
 }
 
-// Step 4b: one thread per bucket: empty buckets become the identity; a bucket split over a few
-// slices gets the sum of its pieces (slot rule as in k_accumulate).  Buckets split over more than
-// HEAVY_PIECES slices (skewed scalars) are queued for k_fix_heavy.
+// Per-slot geometry of the deferred fix-up (passed by value): T = threads the accumulation of the
+// queued MSM in that slot ran with.
+constexpr int MSM_QUEUE = 16;
+struct TailSlots {
+  uint32_t T[MSM_QUEUE];
+};
+
+// Step 4b (deferred, batched: blockIdx.z = queued MSM): one thread per bucket: empty buckets become
+// the identity; a bucket split over a few slices gets the sum of its pieces (slot rule as in
+// k_accumulate).  Buckets split over more than HEAVY_PIECES slices (skewed scalars)
+// are queued for k_fix_heavy.
 constexpr uint32_t HEAVY_PIECES = 8;
 template <class F>
 __global__ void __launch_bounds__(128)
-k_fix_partials(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums,
-               const XYZZ<F>* __restrict__ partial, uint32_t nbuckets, uint32_t T,
-               uint32_t* __restrict__ heavy_count, uint32_t* __restrict__ heavy_list) {
+k_fix_partials(const uint32_t* __restrict__ offsets_all, XYZZ<F>* __restrict__ bucket_sums_all,
+               const XYZZ<F>* __restrict__ partial_all, uint32_t nbuckets, size_t partial_stride, TailSlots slots,
+               uint32_t* __restrict__ heavy_all, size_t heavy_stride) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
+  const int z = blockIdx.z;
+  const uint32_t* offsets = offsets_all + (size_t)z * (nbuckets + 1);
+  XYZZ<F>* bucket_sums = bucket_sums_all + (size_t)z * nbuckets;
+  const XYZZ<F>* partial = partial_all + (size_t)z * partial_stride;
+  uint32_t* heavy = heavy_all + (size_t)z * heavy_stride;
+  const uint32_t T = slots.T[z];
   const uint32_t E = offsets[nbuckets];
   const uint32_t lo = offsets[b], hi = offsets[b + 1];
   if (lo == hi) { store_vec(&bucket_sums[b], XYZZ<F>::inf()); return; }
   const uint32_t per = (E + T - 1) / T;
   const uint32_t t_first = lo / per, t_last = (hi - 1) / per;
   if (t_first == t_last) return;  // written whole by its slice
-  if (t_last - t_first + 1 > HEAVY_PIECES) { heavy_list[atomicAdd(heavy_count, 1u)] = b; return; }
+  if (t_last - t_first + 1 > HEAVY_PIECES) { heavy[1 + atomicAdd(heavy, 1u)] = b; return; }
   XYZZ<F> acc = XYZZ<F>::inf();
   for (uint32_t t = t_first; t <= t_last; t++) {
     const uint32_t slot = ((uint64_t)t * per >= lo) ? 0 : 1;
@@ -316,21 +331,29 @@ k_fix_partials(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucke
   store_vec(&bucket_sums[b], acc);
 }
 
-// Step 4c: heavy buckets, one BLOCK each (grid-stride over the queue): threads stride over the
-// pieces, a shared-memory tree adds the per-thread sums: pieces / blockDim + log2(blockDim)
-// sequential additions (a 2^20-point MSM whose scalars are half ones has a 17 000-piece bucket).
+// Step 4c: heavy buckets, one BLOCK each (grid-stride over the queue; blockIdx.z = queued MSM):
+// threads stride over the pieces, a shared-memory tree adds the per-thread sums: pieces / blockDim +
+// log2(blockDim) sequential additions (a 2^20-point MSM whose scalars are half ones has a
+// 17 000-piece bucket).
 template <class F>
 __global__ void __launch_bounds__(256)
-k_fix_heavy(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums,
-            const XYZZ<F>* __restrict__ partial, uint32_t nbuckets, uint32_t T,
-            const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
+k_fix_heavy(const uint32_t* __restrict__ offsets_all, XYZZ<F>* __restrict__ bucket_sums_all,
+            const XYZZ<F>* __restrict__ partial_all, uint32_t nbuckets, size_t partial_stride, TailSlots slots,
+            const uint32_t* __restrict__ heavy_all, size_t heavy_stride) {
   extern __shared__ uint4 smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  const uint32_t count = *heavy_count;
+  const int z = blockIdx.z;
+  const uint32_t* heavy = heavy_all + (size_t)z * heavy_stride;
+  const uint32_t count = heavy[0];
+  if (count == 0) return;   // block-uniform
+  const uint32_t* offsets = offsets_all + (size_t)z * (nbuckets + 1);
+  XYZZ<F>* bucket_sums = bucket_sums_all + (size_t)z * nbuckets;
+  const XYZZ<F>* partial = partial_all + (size_t)z * partial_stride;
+  const uint32_t T = slots.T[z];
   const uint32_t E = offsets[nbuckets];
   const uint32_t per = (E + T - 1) / T;
   for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {   // block-uniform
-    const uint32_t b = heavy_list[q];
+    const uint32_t b = heavy[1 + q];
     const uint32_t lo = offsets[b], hi = offsets[b + 1];
     const uint32_t t_first = lo / per, t_last = (hi - 1) / per;
     XYZZ<F> acc = XYZZ<F>::inf();
@@ -421,7 +444,6 @@ k_reduce_tree(const XYZZ<F>* __restrict__ in, uint32_t n_in, size_t in_stride, X
 }
 
 // Output slots of the queued MSMs (passed by value to the batched tail kernels).
-constexpr int MSM_QUEUE = 16;
 template <class F>
 struct TailOutputs {
   XYZZ<F>* result[MSM_QUEUE];   // XYZZ sum (always set: caller's slot or table scratch)
@@ -554,26 +576,23 @@ struct BaseTable {
   DevBuf<Affine<F>> pts;     // n points, or W * n when precomputed (window-major)
   DevBuf<uint8_t> skip;      // 1 = identity base
   // workspace (reused by every MSM on this table; calls on one table are stream-ordered)
-  DevBuf<uint32_t> counts, offsets, cursor, tile_sums, entries, heavy;   // heavy[0] = queue length, then the queue
+  DevBuf<uint32_t> counts, cursor, tile_sums, entries;   // counts is all zero between MSMs (k_scan_apply clears it)
+  DevBuf<uint32_t> offsets, heavy;   // one slot per queued MSM: bucket offsets (nb + 1); heavy[0] = queue length, then the queue
   // Deferred tails.  The latency-bound end of an MSM (bucket reduction, window combine, affine
   // conversion: ~40 dependent point operations) costs the same wall time for one MSM as for a batch,
   // so a pipelined table queues up to MSM_QUEUE accumulated MSMs (one bucket_sums slot each) and
   // finishes them with ONE batched launch sequence on the caller's stream (flush / join).
-  DevBuf<XYZZ<F>> bucket_sums, partial, chunk_out, tree_tmp, window_sums;   // MSM_QUEUE slots each (partial: 1)
+  DevBuf<XYZZ<F>> bucket_sums, partial, chunk_out, tree_tmp, window_sums;   // queue_cap slots each
+  TailSlots slot_geom{};     // accumulation threads of every queued MSM (for the deferred fix-up)
+  size_t partial_stride = 0, heavy_stride = 0;
   uint32_t acc_blocks = 0;   // persistent grid of k_accumulate: resident blocks per SM x SMs
   int acc_variant = 0;       // ZKB200_ACC_VARIANT[_G2]: see build_tables (9 / 5 = cp.async-staged defaults for G1 / G2)
   template <class Fn> void acc_dispatch(Fn&& fn);
   int acc_occupancy();
-  void acc_launch(uint32_t grid, XYZZ<F>* bsum, cudaStream_t st);
+  void acc_launch(uint32_t grid, const uint32_t* off, XYZZ<F>* bsum, XYZZ<F>* part, cudaStream_t st);
   int queued = 0;
   int queue_cap = 0;         // bucket buffers currently allocated (1 unless pipelined)
   TailOutputs<F> outs{};
-  // batched-affine accumulation (msm_ba.cuh), selected by ZKB200_BATCHED_AFFINE
-  bool use_ba = false;
-  int ba_rounds = 0;
-  DevBuf<Affine<F>> ba_buf[2];
-  DevBuf<F> ba_scratch;
-  DevBuf<uint32_t> ba_off[2], ba_counts, ba_dummy;
   bool pipelined = false;    // false: every run() flushes immediately (plain stream order)
 
   static MsmConfig choose_config(uint32_t n, bool precompute, int force_c);
@@ -582,8 +601,9 @@ struct BaseTable {
   void build_tables(cudaStream_t st);
   // d_scalars: count * 32 B canonical little-endian; uses bases [first, first + count).
   // d_result (nullable) receives the XYZZ sum, d_out_bytes (nullable) the RAW + COMP bytes.
+  // d_err (nullable): set to 1 when a scalar is not canonical (>= r).
   void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes, cudaStream_t st,
-           uint32_t first = 0);
+           uint32_t first = 0, int* d_err = nullptr);
   // finish every queued MSM on `st` (batched tail); results are valid in stream order afterwards
   void join(cudaStream_t st);
   // pipelined = queue up to MSM_QUEUE tails (allocates that many bucket buffers on first use)
@@ -591,10 +611,13 @@ struct BaseTable {
   void ensure_queue(int slots);
   // forget every queued tail (after an error between run() and join(): the queued output pointers
   // may refer to buffers that are being unwound); the caller drains the streams first
-  void abort_queue() { queued = 0; }
+  void abort_queue() {
+    queued = 0;
+    if (counts.p) cudaMemset(counts.p, 0, counts.bytes());   // a run cut short may have left the histogram dirty
+  }
   // stage timing (bench.py's roofline leg): when `profile` is set, run() brackets its stages with
   // CUDA events; stage_ms() reads them after the streams have drained.
-  // stages: 0 digits+scan+scatter, 1 accumulate (+ partial fix-up), 2 bucket reduce, 3 combine+finalize
+  // stages: 0 digits+scan+scatter, 1 accumulate, 2 partial fix-up + bucket reduce, 3 combine+finalize
   bool profile = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void stage_ms(float out[4]);

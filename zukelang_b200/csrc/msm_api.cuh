@@ -143,8 +143,7 @@ void table_msm_host(TableHandle<T>* h, const uint8_t* scalars, size_t n, uint8_t
     TablePart<T>& P = *h->parts[0];
     P.d_scalars.ensure(n * 8);
     ZK_CUDA(cudaMemcpyAsync(P.d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st0));
-    k_check_scalars<<<cdiv(n, 256), 256, 0, st0>>>(P.d_scalars.p, (uint32_t)n, h->d_err.p);
-    P.table.run(P.d_scalars.p, (uint32_t)n, h->d_result.p, h->d_out.p, st0);
+    P.table.run(P.d_scalars.p, (uint32_t)n, h->d_result.p, h->d_out.p, st0, 0, h->d_err.p);
     P.table.join(st0);
   } else {
     h->d_gather.ensure(active);
@@ -157,8 +156,7 @@ void table_msm_host(TableHandle<T>* h, const uint8_t* scalars, size_t n, uint8_t
       P.d_scalars.ensure((size_t)cnt * 8);
       ZK_CUDA(cudaStreamWaitEvent(st, h->ready, 0));
       ZK_CUDA(cudaMemcpyAsync(P.d_scalars.p, scalars + (size_t)P.lo * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, st));
-      k_check_scalars<<<cdiv(cnt, 256), 256, 0, st>>>(P.d_scalars.p, cnt, h->d_err.p);
-      P.table.run(P.d_scalars.p, cnt, h->d_gather.p + p, nullptr, st);
+      P.table.run(P.d_scalars.p, cnt, h->d_gather.p + p, nullptr, st, 0, h->d_err.p);
       P.table.join(st);
       ZK_CUDA(cudaEventRecord(P.done, st));
     }
@@ -226,9 +224,9 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
       ZK_CUDA(cudaEventRecord(B.copied[b], cs));
       ZK_CUDA(cudaStreamWaitEvent(st, B.copied[b], 0));
       if (tm) ZK_CUDA(cudaEventRecord(B.t_k0[i], st));
-      k_check_scalars<<<cdiv(cnt, 256), 256, 0, st>>>(B.d_sc[b].p, cnt, h->d_err.p);
-      if (multi) P.table.run(B.d_sc[b].p, cnt, h->d_gather.p + i * active + p, nullptr, st);
-      else P.table.run(B.d_sc[b].p, cnt, nullptr, h->d_out.p + i * OUT, st);
+      // (the canonical-scalar check rides in the first digit pass)
+      if (multi) P.table.run(B.d_sc[b].p, cnt, h->d_gather.p + i * active + p, nullptr, st, 0, h->d_err.p);
+      else P.table.run(B.d_sc[b].p, cnt, nullptr, h->d_out.p + i * OUT, st, 0, h->d_err.p);
       ZK_CUDA(cudaEventRecord(B.consumed[b], st));
       if (tm) { ZK_CUDA(cudaEventRecord(B.t_k1[i], st)); B.steps_timed = (int)i + 1; }
     }
@@ -313,19 +311,34 @@ __global__ void k_sum_raw(const uint8_t* __restrict__ raw, uint32_t k, XYZZ<type
   store_vec(out, acc);
 }
 
-// batched form for the shard gather: out[q] = sum_r points[r * batch + q], one block per q
+// batched form for the shard gather: out[q] = sum_r points[r * batch + q], one block per q.
+// Asynchronous (no place to return an error): a partial that does not parse POISONS its output
+// slot (every byte 0xff, which no parser accepts) instead of being skipped.
 template <class T>
 __global__ void k_sum_strided(const uint8_t* __restrict__ raw, uint32_t k, uint32_t batch, uint8_t* __restrict__ out) {
   if (threadIdx.x) return;
   const uint32_t q = blockIdx.x;
   XYZZ<typename T::F> acc = XYZZ<typename T::F>::inf();
+  bool bad = false;
   for (uint32_t r = 0; r < k; r++) {
     Affine<typename T::F> p;
-    if (T::parse(raw + ((size_t)r * batch + q) * T::RAW, p)) continue;
+    if (T::parse(raw + ((size_t)r * batch + q) * T::RAW, p)) { bad = true; continue; }
     acc.madd(p);
   }
+  uint8_t* o = out + (size_t)q * (T::RAW + T::COMP);
+  if (bad) {
+    for (int i = 0; i < T::RAW + T::COMP; i++) o[i] = 0xff;
+    return;
+  }
   Affine<typename T::F> a = acc.to_affine();
-  T::serialize(a, out + (size_t)q * (T::RAW + T::COMP));
+  T::serialize(a, o);
+}
+
+// poison marker for the asynchronous single sum (see k_sum_strided)
+template <class T>
+__global__ void k_poison_if(const int* __restrict__ err, uint8_t* __restrict__ out) {
+  if (*err == 0) return;
+  for (int i = threadIdx.x; i < T::RAW + T::COMP; i += blockDim.x) out[i] = 0xff;
 }
 
 template <class T>
@@ -344,9 +357,13 @@ int api_sum_dev(const void* d_points, size_t k, void* d_out, void* stream) {
   ZK_REQUIRE(d_points && d_out && k > 0 && k <= 4096, ZK_EARG, "sum_dev: bad arguments");
   cudaStream_t st = stream ? (cudaStream_t)stream : default_stream();
   static thread_local DevBuf<XYZZ<typename T::F>> scratch;
+  static thread_local DevBuf<int> flag;
   scratch.ensure(1);
-  k_sum_raw<T><<<1, 32, 0, st>>>((const uint8_t*)d_points, (uint32_t)k, scratch.p, nullptr);
+  flag.ensure(1);
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), st));
+  k_sum_raw<T><<<1, 32, 0, st>>>((const uint8_t*)d_points, (uint32_t)k, scratch.p, flag.p);
   finalize_points<T>(scratch.p, 1, (uint8_t*)d_out, st);
+  k_poison_if<T><<<1, 32, 0, st>>>(flag.p, (uint8_t*)d_out);
   ZK_API_END
 }
 

@@ -2,11 +2,7 @@
 #pragma once
 #include <algorithm>
 #include "msm.cuh"
-#include "msm_ba.cuh"
 
-#ifndef ZK_BATCHED_AFFINE_DEFAULT
-#define ZK_BATCHED_AFFINE_DEFAULT 0
-#endif
 #ifndef ZK_ACC_VARIANT_DEFAULT
 #define ZK_ACC_VARIANT_DEFAULT 9
 #endif
@@ -97,7 +93,6 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   }
   uint32_t nb = cfg.nbuckets();
   counts.alloc(nb);
-  offsets.alloc(nb + 1);
   cursor.alloc(nb);
   tile_sums.alloc(cdiv(nb, SCAN_TILE) + 1);
   entries.alloc((size_t)n * cfg.W);
@@ -114,42 +109,20 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
     if (per_sm < 1) per_sm = 1;
     acc_blocks = (uint32_t)per_sm * (uint32_t)sm_count();
   }
-  uint32_t cpw = cfg.B / cfg.L;
-  heavy.alloc((size_t)acc_blocks * 128 / 4 + 2);
-  partial.alloc(2 * (size_t)acc_blocks * 128);
-  (void)cpw;
+  ZK_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), st));   // kept zero between MSMs by k_scan_apply
+  partial_stride = 2 * (size_t)acc_blocks * ACC_THREADS;
+  heavy_stride = (size_t)acc_blocks * ACC_THREADS / 4 + 2;
   queued = 0;
   queue_cap = 0;
   pipelined = false;
   ensure_queue(1);
   if (env_int("ZKB200_PIPELINE", 0) != 0) set_pipelined(true);
-  use_ba = env_int("ZKB200_BATCHED_AFFINE", ZK_BATCHED_AFFINE_DEFAULT) != 0;
-  if (use_ba) {
-    uint64_t E = (uint64_t)n * cfg.W;
-    uint64_t avg = E / nb + 1;
-    int R = 1;
-    while ((1ull << R) < 2 * avg) R++;
-    R += 1;
-    int env_r = env_int("ZKB200_BA_ROUNDS", -1);
-    if (env_r >= 0) R = env_r;
-    if (R > 24) R = 24;
-    ba_rounds = R;
-    // per-round output bound b_{r+1} = b_r / 2 + nb + 1 starts at E / 2 + nb + 1 and tends to 2 nb + 2
-    uint64_t out0 = std::max<uint64_t>(E / 2 + nb + 2, 2ull * nb + 4);
-    uint64_t out1 = std::max<uint64_t>(out0 / 2 + nb + 2, 2ull * nb + 4);
-    ba_buf[0].alloc(out0);
-    ba_buf[1].alloc(out1);
-    ba_scratch.alloc((size_t)BA_K * (cdiv(out0, BA_K) + 1));
-    ba_off[0].alloc(nb + 1);
-    ba_off[1].alloc(nb + 1);
-    ba_counts.alloc(nb);
-    ba_dummy.alloc(nb);
-  }
+  ZK_CUDA(cudaStreamSynchronize(st));
 }
 
 template <class T>
 void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes,
-                       cudaStream_t st, uint32_t first) {
+                       cudaStream_t st, uint32_t first, int* d_err) {
   ZK_REQUIRE(count > 0 && (uint64_t)first + count <= n, ZK_EARG, "scalar range exceeds the base table");
   const uint32_t nb = cfg.nbuckets();
   if (queued >= queue_cap) join(st);
@@ -157,58 +130,24 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   if (profile && !ev[0])
     for (auto& e : ev) ZK_CUDA(cudaEventCreate(&e));
   auto mark = [&](int i) { if (profile) ZK_CUDA(cudaEventRecord(ev[i], st)); };
-  // ---- sort and accumulate -----------------------------------------------------------------
+  // ---- sort and accumulate: five launches, no memsets (the histogram comes back zeroed) ----------
   mark(0);
-  ZK_CUDA(cudaMemsetAsync(counts.p, 0, nb * sizeof(uint32_t), st));
-  k_digits<false><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, first, n, cfg, counts.p, nullptr);
+  uint32_t* off = offsets.p + (size_t)slot * (nb + 1);
+  k_digits<false><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, first, n, cfg, counts.p, nullptr, d_err);
   uint32_t ntiles = cdiv(nb, SCAN_TILE);
   k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p);
-  k_scan_spine<<<1, 1024, 0, st>>>(tile_sums.p, ntiles);
-  k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p, offsets.p, cursor.p);
-  k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, first, n, cfg, cursor.p, entries.p);
+  k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p, off, cursor.p);
+  k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, first, n, cfg, cursor.p, entries.p, nullptr);
   mark(1);
-  XYZZ<F>* bsum = bucket_sums.p + (size_t)slot * nb;
-  if (use_ba) {
-    // rounds of pairwise affine additions inside the buckets, shared inversions (msm_ba.cuh)
-    const uint32_t* in_off = offsets.p;
-    uint64_t bound = (uint64_t)count * cfg.W;       // entries of round 0
-    for (int r = 0; r < ba_rounds; r++) {
-      uint32_t* out_off = ba_off[r & 1].p;
-      k_ba_next_counts<<<cdiv(nb, 256), 256, 0, st>>>(in_off, nb, ba_counts.p);
-      k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(ba_counts.p, nb, tile_sums.p);
-      k_scan_spine<<<1, 1024, 0, st>>>(tile_sums.p, ntiles);
-      k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(ba_counts.p, nb, tile_sums.p, out_off, ba_dummy.p);
-      bound = bound / 2 + nb + 1;
-      uint32_t nthr = cdiv(bound, BA_K);
-      if (r == 0)
-        k_ba_round<F, true><<<cdiv(nthr, 128), 128, 0, st>>>(pts.p, entries.p, nullptr, in_off, out_off, nb, ba_buf[0].p,
-                                                             ba_scratch.p, nthr);
-      else
-        k_ba_round<F, false><<<cdiv(nthr, 128), 128, 0, st>>>(nullptr, nullptr, ba_buf[(r - 1) & 1].p, in_off, out_off, nb,
-                                                              ba_buf[r & 1].p, ba_scratch.p, nthr);
-      in_off = out_off;
-    }
-    if (ba_rounds == 0)
-      k_ba_finish<F, true><<<cdiv(nb, 128), 128, 0, st>>>(pts.p, entries.p, nullptr, in_off, nb, bsum);
-    else
-      k_ba_finish<F, false><<<cdiv(nb, 128), 128, 0, st>>>(nullptr, nullptr, ba_buf[(ba_rounds - 1) & 1].p, in_off, nb, bsum);
-  } else {
   // one wave at most; for small inputs fewer blocks, so that a slice still holds >= 16 entries
   // (otherwise the partial fix-up, not the mixed adds, would end up doing the additions)
-  uint32_t grid = cdiv((uint64_t)count * cfg.W, 16 * 128);
+  uint32_t grid = cdiv((uint64_t)count * cfg.W, 16 * ACC_THREADS);
   if (grid > acc_blocks) grid = acc_blocks;
   if (grid < 1) grid = 1;
-  acc_launch(grid, bsum, st);
-  ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));
-  k_fix_partials<F><<<cdiv(nb, 128), 128, 0, st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p, heavy.p + 1);
-  {
-    const int ht = sizeof(XYZZ<F>) > 192 ? 128 : 256;   // 48 KB of shared memory either way
-    k_fix_heavy<F><<<sm_count(), ht, ht * sizeof(XYZZ<F>), st>>>(offsets.p, bsum, partial.p, nb, grid * 128, heavy.p,
-                                                                 heavy.p + 1);
-  }
-  }
+  acc_launch(grid, off, bucket_sums.p + (size_t)slot * nb, partial.p + (size_t)slot * partial_stride, st);
+  slot_geom.T[slot] = grid * ACC_THREADS;
   mark(2);
-  // ---- queue the tail ------------------------------------------------------------------------
+  // ---- queue the tail (partial fix-up, bucket reduction, window combine, wire bytes) -------------
   outs.result[slot] = d_result ? d_result : window_sums.p + (size_t)slot * (cfg.nwb + 1) + cfg.nwb;
   outs.bytes[slot] = d_out_bytes;
   queued++;
@@ -242,9 +181,9 @@ int BaseTable<T>::acc_occupancy() {
   return per_sm;
 }
 template <class T>
-void BaseTable<T>::acc_launch(uint32_t grid, XYZZ<F>* bsum, cudaStream_t st) {
+void BaseTable<T>::acc_launch(uint32_t grid, const uint32_t* off, XYZZ<F>* bsum, XYZZ<F>* part, cudaStream_t st) {
   acc_dispatch([&](auto kern, size_t smem) {
-    kern<<<grid, ACC_THREADS, smem, st>>>(pts.p, entries.p, offsets.p, bsum, partial.p, cfg.nbuckets());
+    kern<<<grid, ACC_THREADS, smem, st>>>(pts.p, entries.p, off, bsum, part, cfg.nbuckets());
   });
 }
 
@@ -255,6 +194,9 @@ void BaseTable<T>::ensure_queue(int slots) {
   const uint32_t nb = cfg.nbuckets();
   const uint32_t cpw = cfg.B / cfg.L;
   bucket_sums.alloc((size_t)slots * nb);
+  offsets.alloc((size_t)slots * (nb + 1));
+  partial.alloc((size_t)slots * partial_stride);
+  heavy.alloc((size_t)slots * heavy_stride);
   chunk_out.alloc((size_t)slots * cfg.nwb * cpw);
   tree_tmp.alloc((size_t)slots * cfg.nwb * cdiv(cpw, TAIL_THREADS) + 1);
   window_sums.alloc((size_t)slots * (cfg.nwb + 1));
@@ -279,6 +221,15 @@ void BaseTable<T>::join(cudaStream_t st) {
   MsmConfig rc = cfg;
   if (Q >= 3 && env_int("ZKB200_REDUCE_CHUNK", 0) <= 0) { rc.L = 16; while ((uint32_t)rc.L > rc.B) rc.L >>= 1; }
   const uint32_t cpw = rc.B / rc.L;
+  // deferred fix-up of the buckets that were split over several accumulation slices, all queued MSMs at once
+  ZK_CUDA(cudaMemset2DAsync(heavy.p, heavy_stride * sizeof(uint32_t), 0, sizeof(uint32_t), Q, st));   // heavy[z][0] = 0
+  k_fix_partials<F><<<dim3(cdiv(nb, 128), 1, Q), 128, 0, st>>>(offsets.p, bucket_sums.p, partial.p, nb, partial_stride, slot_geom,
+                                                               heavy.p, heavy_stride);
+  {
+    const int ht = sizeof(XYZZ<F>) > 192 ? 128 : 256;   // 48 KB of shared memory either way
+    k_fix_heavy<F><<<dim3(sm_count(), 1, Q), ht, ht * sizeof(XYZZ<F>), st>>>(offsets.p, bucket_sums.p, partial.p, nb, partial_stride,
+                                                                             slot_geom, heavy.p, heavy_stride);
+  }
   k_reduce_chunks<F><<<dim3(cdiv((size_t)cpw * cfg.nwb, TAIL_THREADS), 1, Q), TAIL_THREADS, 0, st>>>(bucket_sums.p, rc,
                                                                                                      chunk_out.p);
   {
@@ -326,7 +277,7 @@ BaseTable<T>::~BaseTable() {
 template <class T>
 size_t BaseTable<T>::device_bytes() const {
   return pts.bytes() + skip.bytes() + counts.bytes() + offsets.bytes() + cursor.bytes() + tile_sums.bytes() +
-         entries.bytes() + heavy.bytes() + bucket_sums.bytes() + partial.bytes() + chunk_out.bytes() + tree_tmp.bytes() + window_sums.bytes() + ba_buf[0].bytes() + ba_buf[1].bytes() + ba_scratch.bytes();
+         entries.bytes() + heavy.bytes() + bucket_sums.bytes() + partial.bytes() + chunk_out.bytes() + tree_tmp.bytes() + window_sums.bytes();
 }
 
 template <class T>
