@@ -256,7 +256,8 @@ def run_gpu_arm(args):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=600))
     zk = _lib.lib()
     sampler = ClockSampler(local_rank)
     sampler.start()                                     # nvidia-smi takes a second to come up: start it first
@@ -435,11 +436,48 @@ def run_gpu_arm(args):
                      "compute_stream_stall_ms_total": sum(max(0.0, tm[i][2] - tm[i - 1][3]) for i in range(1, len(tm))),
                      "first_kernel_after_ms": tm[0][2], "last_kernel_done_ms": tm[-1][3]}
 
+    # ---- secondary legs (every rank takes part; each is exact-checked) ---------------------------
+    _lib.check(zk.zk_table_free(handle.value))
+    host0 = batches[0]["host"]                             # kept for the CPU baseline leg
+    del batches, d_ring
+    torch.cuda.empty_cache()
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    legs = {}
+
+    def leg(name, fn):
+        t0 = time.time()
+        try:
+            legs[name] = fn()
+        except Exception as e:                                 # never lose the headline line
+            legs[name] = {"error": repr(e)}
+        legs.setdefault("leg_seconds", {})[name] = round(time.time() - t0, 1)
+
+    if args.groth16:
+        # second half of BASELINE.json's metric: Groth16 proofs/s on the synthetic circuits of configs[2]
+        # (2^16) and configs[4] (2^20, G2 B-query included; sharded by base range over the N ranks):
+        # host witness in, proof bytes out, every proof checked against the closed-form trapdoor identity
+        import bench_groth16
+
+        def g16():
+            out = []
+            for spec in args.groth16:
+                ln, circ = spec.split(":")
+                out.append(bench_groth16.run(zk, int(ln), 3, circ, dist, quiet=True))
+            return out
+        leg("groth16", g16)
+    if args.sweep:
+        import bench_legs
+        leg("sweep", lambda: bench_legs.sweep(zk, _lib, torch, dist, rank, world, side, args.sweep, SEED_SCALARS))
+    if world == 1 and not args.no_shapes:
+        import bench_legs
+        leg("oneshot", lambda: bench_legs.oneshot(zk, _lib, torch, side, args.logn, SEED_SCALARS, peak_mac32))
+        leg("roofline_g2", lambda: bench_legs.g2_roofline(zk, _lib, torch, side, min(args.logn, 20), SEED_SCALARS, peak_mac32))
+
     if rank == 0:
         c, W = int(info[0]), int(info[1])
-        # kernels of libzkb200 launched in the timed region: 8 per MSM (2 digit passes, 3 scan kernels,
-        # accumulate, 2 partial fix-ups) + one batched tail per group (reduce chunks, tree levels,
-        # combine+finalize) + the shard sum for N > 1
+        # kernels of libzkb200 launched in the timed region: 5 per MSM (digit count pass with the scalar
+        # check, 2 scan kernels, digit scatter pass, accumulate) + one batched tail per group (2 partial
+        # fix-ups, reduce chunks, tree levels, combine+finalize) + the shard sum for N > 1
         group = QUEUE if pipelined else 1
         groups = (args.steps + group - 1) // group
         cpw = (1 << (c - 1)) // (16 if (pipelined and min(group, args.steps) >= 3) else 4)
@@ -449,7 +487,7 @@ def run_gpu_arm(args):
             cnt = (cnt + 63) // 64
             if cnt == 1:
                 break
-        gpu_launches = 8 * args.steps + groups * (2 + levels + (1 if world > 1 else 0))
+        gpu_launches = 5 * args.steps + groups * (4 + levels + (1 if world > 1 else 0))
         acc_avg = sum(acc_ms) / len(acc_ms)
         achieved = n * MAC32_PER_POINT / (acc_avg * 1e-3) / 1e12
         peaks = {}
@@ -491,20 +529,11 @@ def run_gpu_arm(args):
                                  "frac": algo_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         }
-        if world == 1 and args.groth16_logn:
-            # second half of BASELINE.json's metric: Groth16 proofs/s on synthetic multiply-chain
-            # circuits (configs[2] at 2^16, configs[4] at 2^20), host witness in, proof bytes out,
-            # each proof checked against the closed-form trapdoor identity
-            try:
-                sys.path.insert(0, os.path.join(ROOT, "tools"))
-                import bench_groth16
-                line["groth16"] = [bench_groth16.run(zk, ln, 3, quiet=True) for ln in args.groth16_logn]
-            except Exception as e:                                 # never lose the headline line
-                line["groth16"] = {"error": repr(e)}
+        line.update({k: v for k, v in legs.items()})
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             sample = 1 << 15
-            sc_raw = batches[0]["host"].numpy().tobytes()[:sample * 32]
+            sc_raw = host0.numpy().tobytes()[:sample * 32]
             secs, out = cpu_fold_msm(bases[:sample * 96].tobytes(), sc_raw, sample, threads)
             line["cpu_baseline"] = {"value": sample / secs / 1e6, "unit": "Mpts/s", "cores": threads, "kind": "port",
                                     "sample": "first 2^15 of the 2^20 points, oracle/c fold of double-and-add scalar muls "
@@ -512,12 +541,11 @@ def run_gpu_arm(args):
             try:                                                   # informational; never lose the headline line
                 n_timed = min(1 << 18, n_total)
                 line["cpu_pippenger"] = cpu_pippenger_line(bases[:n_timed * 96].tobytes(),
-                                                           batches[0]["host"].numpy().tobytes()[:n_timed * 32],
+                                                           host0.numpy().tobytes()[:n_timed * 32],
                                                            sample, out, n_timed, threads)
             except Exception as e:
                 line["cpu_pippenger"] = {"error": repr(e)}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
-    _lib.check(zk.zk_table_free(handle.value))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -540,8 +568,11 @@ def main():
     ap.add_argument("--logn", type=int, default=LOG_N)
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--groth16-logn", type=int, nargs="*", default=[16],
-                    help="also time Groth16 prove at these constraint counts (N = 1 only)")
+    ap.add_argument("--groth16", nargs="*", default=["16:mulchain", "20:mulchain", "20:r1cs"],
+                    help="also time Groth16 prove: log2(constraints):circuit (mulchain | r1cs), on all N ranks")
+    ap.add_argument("--sweep", type=int, nargs="*", default=list(range(16, 25)),
+                    help="G1 MSM sweep sizes (log2 points, BASELINE configs[3]); empty = skip")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the one-shot and G2 legs (N = 1)")
     ap.add_argument("--no-pipeline", action="store_true", help="plain stream order between steps")
     args = ap.parse_args()
     if args.warmup < 3:

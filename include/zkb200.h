@@ -227,6 +227,10 @@ typedef struct {
 
 #define ZK_PINOCCHIO_PROOF_OUT (6 * ZK_G1_OUT + 2 * ZK_G2_OUT)
 
+/* Device time (ms, CUDA events on the primary device's stream: first upload to last download) of
+ * the last zk_groth16_prove* call on this key; for bench.py. */
+int zk_groth16_last_device_ms(uint64_t pk, float *ms);
+
 int zk_pinocchio_pk_load(const zk_pinocchio_pkey *pk, int shard_index, int shard_count, uint64_t *handle);
 /* d = dv | dw | dy (3 * 32 B, the draws of pinocchio.ml:428-430) selects ZK.prove (:559-561);
  * d = NULL selects NonZK.prove (:536-538).  proof_out holds vv | ww | yy | h | vavv | waww |

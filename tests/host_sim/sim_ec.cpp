@@ -16,10 +16,7 @@ static void ec_op(int op, const uint32_t* a, const uint32_t* b, const uint32_t* 
     case 2: r = A.dbl(); break;
     case 3: r = scalar_mul(A, k); break;
     case 4: r = XYZZ<F>::dbl_affine(Q); break;
-    case 5:   // Fp only (Mont::mul2)
-      r = A;
-      if constexpr (sizeof(F) == sizeof(Fp)) r.madd_paired(Q); else r.madd(Q);
-      break;
+    case 5: r = A; r.madd_paired(Q); break;   // interleaved product pairs (Mont::mul2 / Fp2::mul2)
   }
   Affine<F> aff = r.to_affine();
   memcpy(out, &aff, sizeof(aff));

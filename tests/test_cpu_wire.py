@@ -86,3 +86,22 @@ def test_documents_of_the_wrong_shape_are_rejected(doc):
         wire.decode(wire.Groth16Wire.PROOF, wire.loads(doc))
     with pytest.raises(ValueError):
         wire.decode(wire.Map_("Fr"), wire.loads(b'[["x","1"]]'))
+
+
+def test_bench_circuit_generators_match_the_oracle():
+    """tools/bench_groth16.py builds its synthetic circuits without the oracle (product-side code);
+    they must be the circuits the parity tests prove on (oracle/zk.py generators)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bench_groth16 as BG
+    from oracle import zk as Z
+    for name, ogen in (("mulchain", Z.circuit_mulchain), ("r1cs", Z.circuit_random_r1cs)):
+        for n in (2, 7, 64):
+            oc, owit = ogen(n)
+            pc, pwit = BG.CIRCUITS[name](n)
+            assert [(dict(g.lhs), dict(g.l), dict(g.r)) for g in oc.gates] == pc.gates
+            assert list(oc.inputs_public) == list(pc.inputs_public) and list(oc.outputs) == list(pc.outputs)
+            assert sorted(oc.mids) == sorted(pc.mids) and oc.vars() == pc.variables
+            assert owit(12345) == pwit(12345)
+            assert Z.circuit_check(oc, pwit(99))

@@ -1,7 +1,19 @@
 #!/usr/bin/env python3
-"""Groth16 prove throughput on synthetic multiply-chain circuits (BASELINE configs[2] / [4]):
-c_0 = x, c_{i+1} = c_i * x, n gates, through zk_groth16_prove_r1cs (evaluation-form prover).
-Every run is checked exactly against the closed-form trapdoor identity.  One JSON line per size."""
+"""Groth16 prove throughput on BASELINE.json's synthetic circuits (configs[2] = 2^16, configs[4] = 2^20)
+through zk_groth16_prove_r1cs (the evaluation-form prover):
+
+  mulchain   c_0 = x, c_{i+1} = c_i * x          (the named multiply chain; its B-query scalars W(j) = x
+                                                  are all equal, so the G2 MSM piles into one bucket per window)
+  r1cs       seeded random R1CS, ~3 non-zeros per row: every gate has its own W(j)
+
+Three ways to use the GPUs:
+  one process, one device           python tools/bench_groth16.py --logn 16 20
+  one process, all devices (C ABI)  ZKB200_DEVICES=0,1,2,3,4,5,6,7 python tools/bench_groth16.py --logn 20
+  one process per GPU (torchrun)    torchrun --nproc-per-node 8 tools/bench_groth16.py --logn 20
+    (every rank holds shard (rank, world) of the key; the 576-byte partial results are all-gathered and added)
+
+Every proof that is timed is also checked, byte for byte, against the closed-form trapdoor identity
+(SURVEY.md §8c iv).  One JSON line per (size, circuit).  bench.py imports run() for its `groth16` field."""
 import argparse
 import ctypes
 import json
@@ -16,6 +28,7 @@ from zukelang_b200 import _lib, sparse as S
 from zukelang_b200.curve import R, fr_vector
 
 ONE = ("ONE", 1)
+SEED = 0x47524F54            # "GROT", SURVEY.md §8d config 5
 
 
 def mulchain(n):
@@ -37,145 +50,167 @@ def mulchain(n):
     return circ, witness
 
 
+def random_r1cs(n, seed=SEED):
+    """Gate i: z_i = (a x_p + b x_q + k ONE) * (c x_s + d x_u), operands among the variables defined
+    before gate i, coefficients uniform in Fr.  Same draws as oracle/zk.py:circuit_random_r1cs (the
+    parity tests build the circuit from the oracle's generator; tests/test_cpu_wire.py checks that
+    the two agree)."""
+    rng = random.Random(seed + n)
+    xs = [("input", 2), ("input", 3)]
+    zs = [("_tmp", 4 + i) for i in range(n - 1)] + [("v", 3 + n)]
+    defined = list(xs)
+    gates, plan = [], []
+    for i in range(n):
+        p, q, s_, u = (defined[rng.randrange(len(defined))] for _ in range(4))
+        a, b, c, d, k = (rng.randrange(1, R) for _ in range(5))
+        l, r = {}, {}
+        for var, co in ((p, a), (q, b), (ONE, k)):
+            l[var] = (l.get(var, 0) + co) % R
+        for var, co in ((s_, c), (u, d)):
+            r[var] = (r.get(var, 0) + co) % R
+        gates.append(({zs[i]: 1}, l, r))
+        plan.append((zs[i], sorted(l.items()), sorted(r.items())))
+        defined.append(zs[i])
+    circ = S.SparseCircuit(gates, [ONE], [zs[-1]], xs + zs[:-1])
+
+    def witness(seed2):
+        r2 = random.Random(seed2)
+        sol = {ONE: 1, xs[0]: r2.randrange(R), xs[1]: r2.randrange(R)}
+        for z, l, r in plan:
+            sol[z] = sum(c * sol[v] for v, c in l) % R * (sum(c * sol[v] for v, c in r) % R) % R
+        live = set(circ.variables)
+        return {k: v for k, v in sol.items() if k in live}
+    return circ, witness
+
+
+CIRCUITS = {"mulchain": mulchain, "r1cs": random_r1cs}
+
+
 def fixed_base(zk, group, scalars):
     raw = 96 if group == "g1" else 192
+    if not scalars:
+        return b""
     out = (ctypes.c_uint8 * (raw * len(scalars)))()
     _lib.check(getattr(zk, "zk_%s_fixed_base_mul" % group)(fr_vector(scalars), len(scalars), out))
     return bytes(out)
 
 
-def run(zk, logn, iters, shard=(0, 1), quiet=False):
+def shard_slice(length, idx, cnt):
+    """The rule of csrc/prove.cu:slice."""
+    return length * idx // cnt, length * (idx + 1) // cnt
+
+
+def load_key(zk, circ, td, w, shard):
+    """Key generation for shard (idx, cnt): the trapdoor scalars on the host (Groth16Sparse.keygen_scalars),
+    every group element from the fixed-base kernel — and only the points this shard keeps."""
+    idx, cnt = shard
+    n = circ.n
+    a, b, gm, d, t = td
+    sc = S.Groth16Sparse().keygen_scalars(td, circ, w)
+    mids = sc["mids"]
+    ltd = [sc["ltd"][k] for k in mids]
+    lo_t, hi_t = shard_slice(n, idx, cnt)
+    lo_h, hi_h = shard_slice(n, idx, cnt)          # n_h = n in the evaluation-form key
+    lo_m, hi_m = shard_slice(len(mids), idx, cnt)
+    g1 = fixed_base(zk, "g1", [a, b, d] + sc["lag"][lo_t:hi_t] + sc["hk"][lo_h:hi_h] + ltd[lo_m:hi_m])
+    g2 = fixed_base(zk, "g2", [b, d] + sc["lag"][lo_t:hi_t])
+    pos = {k: i for i, k in enumerate(circ.variables)}
+    idx_arr = (ctypes.c_uint32 * max(len(mids), 1))(*[pos[k] for k in mids])
+    keep = []
+
+    def field(blob, first, count, size, lo):
+        """A list-valued key field of which only [lo, lo + count) is materialised: the C side reads
+        exactly that slice (csrc/prove.cu), so the pointer is biased by -lo elements."""
+        buf = ctypes.create_string_buffer(blob[first * size:(first + count) * size], max(count * size, 1))
+        keep.append(buf)
+        return ctypes.addressof(buf) - lo * size
+
+    nt, nh, nm = hi_t - lo_t, hi_h - lo_h, hi_m - lo_m
+    st = _lib.Groth16PKeyStruct(
+        n=n, m=len(circ.variables), n_mid=len(mids), n_h=n, mid_index=ctypes.addressof(idx_arr),
+        a=field(g1, 0, 1, 96, 0), b1=field(g1, 1, 1, 96, 0), d1=field(g1, 2, 1, 96, 0),
+        ti1=field(g1, 3, nt, 96, lo_t), tiztd=field(g1, 3 + nt, nh, 96, lo_h), ltd_mid=field(g1, 3 + nt + nh, nm, 96, lo_m),
+        b2=field(g2, 0, 1, 192, 0), d2=field(g2, 1, 1, 192, 0), ti2=field(g2, 2, nt, 192, lo_t))
+    h = ctypes.c_uint64()
+    _lib.check(zk.zk_groth16_pk_load(ctypes.byref(st), idx, cnt, ctypes.byref(h)))
+    return h.value, len(mids)
+
+
+def run(zk, logn, iters, circuit="mulchain", dist=None, quiet=False):
+    """Times `iters` proofs (after one warm-up proof).  dist = torch.distributed when the key is sharded
+    over the ranks of a torchrun job; every rank then returns the same record.  Raises on a proof that
+    differs from the closed form."""
+    import torch
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
     n = 1 << logn
     t0 = time.time()
-    circ, witness = mulchain(n)
+    circ, witness = CIRCUITS[circuit](n)
     dom = S.EvalDomain(circ)
-    P = S.Groth16Sparse()
-    rng = random.Random(0x47524F54 + logn)
-    td = tuple(rng.randrange(R) for _ in range(5))
-    a, b, gm, d, t = td
-    sc = P.keygen_scalars(td, circ, dom.w)
-    mids = sc["mids"]
-    g1 = fixed_base(zk, "g1", [a, b, d] + sc["lag"] + sc["hk"] + [sc["ltd"][k] for k in mids])
-    g2 = fixed_base(zk, "g2", [b, d] + sc["lag"])
-    pos = {k: i for i, k in enumerate(circ.variables)}
-    idx = (ctypes.c_uint32 * len(mids))(*[pos[k] for k in mids])
-    o1 = lambda i, cnt: ctypes.create_string_buffer(g1[i * 96:(i + cnt) * 96], cnt * 96)
-    o2 = lambda i, cnt: ctypes.create_string_buffer(g2[i * 192:(i + cnt) * 192], cnt * 192)
-    bufs = dict(a=o1(0, 1), b1=o1(1, 1), d1=o1(2, 1), ti1=o1(3, n), tiztd=o1(3 + n, n), ltd_mid=o1(3 + 2 * n, len(mids)),
-                b2=o2(0, 1), d2=o2(1, 1), ti2=o2(2, n))
-    st = _lib.Groth16PKeyStruct(n=n, m=len(circ.variables), n_mid=len(mids), n_h=n, mid_index=ctypes.addressof(idx),
-                                **{k: ctypes.addressof(v) for k, v in bufs.items()})
-    h = ctypes.c_uint64()
-    _lib.check(zk.zk_groth16_pk_load(ctypes.byref(st), shard[0], shard[1], ctypes.byref(h)))
+    rng = random.Random(SEED + logn)
+    td = tuple(rng.randrange(1, R) for _ in range(5))
+    h, n_mid = load_key(zk, circ, td, dom.w, (rank, world))
     setup_s = time.time() - t0
     sols = []
     for i in range(2):
         sol = witness(rng.randrange(R))
         sols.append((sol, fr_vector(sol[k] for k in circ.variables)))
     out = (ctypes.c_uint8 * _lib.GROTH16_PROOF_OUT)()
-    times = []
-    ok = True
+    wall, dev, ok = [], [], True
+    ms = ctypes.c_float()
+    if dist:
+        from zukelang_b200 import dist as D
     for it in range(iters + 1):
         sol, sol_b = sols[it & 1]
         r, s = rng.randrange(R), rng.randrange(R)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
         t1 = time.perf_counter()
-        _lib.check(zk.zk_groth16_prove_r1cs(h.value, dom.handle, sol_b, r.to_bytes(32, "little"), s.to_bytes(32, "little"), out))
+        _lib.check(zk.zk_groth16_prove_r1cs(h, dom.handle, sol_b, r.to_bytes(32, "little"), s.to_bytes(32, "little"), out))
+        proof = bytes(out)
+        if dist:
+            proof = D.combine_groth16(D.all_gather_bytes(proof))
         dt = time.perf_counter() - t1
+        _lib.check(zk.zk_groth16_last_device_ms(h, ctypes.byref(ms)))
+        if dist:
+            t = torch.tensor([dt, ms.value], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt, dms = float(t[0].item()), float(t[1].item())
+        else:
+            dms = ms.value
         if it:
-            times.append(dt)
-        if it <= 1 and shard == (0, 1):
+            wall.append(dt * 1e3)
+            dev.append(dms)
+        if it <= 1:
             A, B, C = S.closed_form_scalars(td, r, s, circ, dom.w, sol)
-            exp = fixed_base(zk, "g1", [A, C])
-            expb = fixed_base(zk, "g2", [B])
-            b_ = bytes(out)
-            ok &= b_[0:96] == exp[:96] and b_[432:528] == exp[96:] and b_[144:336] == expb
-    best = min(times)
-    rec = {"probe": "groth16", "log_n": logn, "constraints": n, "variables": len(circ.variables),
-           "prove_ms_best": best * 1e3, "prove_ms_all": [x * 1e3 for x in times], "proofs_per_s": 1.0 / best,
-           "exact_ok": bool(ok), "setup_s": setup_s, "circuit": "multiply chain c_{i+1} = c_i * x",
-           "h2d_bytes_per_proof": 32 * len(circ.variables) + 64, "d2h_bytes_per_proof": 576,
-           "msm_points": {"A_g1": n + 3, "C_g1": 3 + 2 * n + len(mids), "B_g2": n + 2}}
-    if not quiet:
+            ok &= proof[0:96] + proof[432:528] == fixed_base(zk, "g1", [A, C]) and proof[144:336] == fixed_base(zk, "g2", [B])
+    med = lambda xs: sorted(xs)[len(xs) // 2]
+    ndev = zk.zk_device_count()
+    rec = {"probe": "groth16", "log_n": logn, "constraints": n, "variables": len(circ.variables), "circuit": circuit,
+           "processes": world, "devices_per_process": ndev,
+           "prove_ms": med(wall), "prove_ms_best": min(wall), "prove_ms_all": wall,
+           "device_ms": med(dev), "device_ms_all": dev, "proofs_per_s": 1e3 / med(wall), "exact_ok": bool(ok),
+           "setup_s": setup_s, "h2d_bytes_per_proof": 32 * len(circ.variables) + 64, "d2h_bytes_per_proof": 576,
+           "timing": "wall clock around the C-ABI prove call%s, median of %d (max over ranks); device_ms = CUDA events inside "
+                     "the call, first upload to last download" % (" + all_gather of the 576-B partials + zk_g*_sum" if dist else "", iters),
+           "msm_points": {"A_g1": n + 3, "C_g1": 3 + 2 * n + n_mid, "B_g2": n + 2}}
+    if not quiet and rank == 0:
         print(json.dumps(rec), flush=True)
-    _lib.check(zk.zk_key_free(h.value))
+    _lib.check(zk.zk_key_free(h))
     dom.free()
-    if quiet:
-        if not ok:
-            raise AssertionError('Groth16 proof differs from the closed form')
-        return rec
-    return ok
-
-
-def run_sharded(zk, logn, iters):
-    """BASELINE configs[4]: one proof sharded by base range over the ranks of a torchrun job.
-    Every rank evaluates the QAP redundantly and proves with shard (rank, world) of the key; the
-    576-byte partial results are all-gathered and added (zk_g1_sum / zk_g2_sum).  Rank 0 checks the
-    proof against the closed form and prints one JSON line."""
-    import torch
-    import torch.distributed as dist
-    from zukelang_b200 import dist as D
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    n = 1 << logn
-    circ, witness = mulchain(n)
-    dom = S.EvalDomain(circ)
-    P = S.Groth16Sparse()
-    rng = random.Random(0x47524F54 + logn)
-    td = tuple(rng.randrange(R) for _ in range(5))
-    a, b, gm, d, t = td
-    sc = P.keygen_scalars(td, circ, dom.w)
-    mids = sc["mids"]
-    g1 = fixed_base(zk, "g1", [a, b, d] + sc["lag"] + sc["hk"] + [sc["ltd"][k] for k in mids])
-    g2 = fixed_base(zk, "g2", [b, d] + sc["lag"])
-    pos = {k: i for i, k in enumerate(circ.variables)}
-    idx = (ctypes.c_uint32 * len(mids))(*[pos[k] for k in mids])
-    o1 = lambda i, cnt: ctypes.create_string_buffer(g1[i * 96:(i + cnt) * 96], cnt * 96)
-    o2 = lambda i, cnt: ctypes.create_string_buffer(g2[i * 192:(i + cnt) * 192], cnt * 192)
-    bufs = dict(a=o1(0, 1), b1=o1(1, 1), d1=o1(2, 1), ti1=o1(3, n), tiztd=o1(3 + n, n), ltd_mid=o1(3 + 2 * n, len(mids)),
-                b2=o2(0, 1), d2=o2(1, 1), ti2=o2(2, n))
-    st = _lib.Groth16PKeyStruct(n=n, m=len(circ.variables), n_mid=len(mids), n_h=n, mid_index=ctypes.addressof(idx),
-                                **{k: ctypes.addressof(v) for k, v in bufs.items()})
-    h = ctypes.c_uint64()
-    _lib.check(zk.zk_groth16_pk_load(ctypes.byref(st), rank, world, ctypes.byref(h)))
-    del g1, g2, bufs
-    sol = witness(rng.randrange(R))
-    sol_b = fr_vector(sol[k] for k in circ.variables)
-    out = (ctypes.c_uint8 * _lib.GROTH16_PROOF_OUT)()
-    times, ok = [], True
-    for it in range(iters + 1):
-        r, s = rng.randrange(R), rng.randrange(R)
-        dist.barrier()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        _lib.check(zk.zk_groth16_prove_r1cs(h.value, dom.handle, sol_b, r.to_bytes(32, "little"), s.to_bytes(32, "little"), out))
-        parts = D.all_gather_bytes(bytes(out))
-        proof = D.combine_groth16(parts)
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        if it:
-            times.append(float(dt.item()))
-        if it <= 1 and rank == 0:
-            A, B, C = S.closed_form_scalars(td, r, s, circ, dom.w, sol)
-            exp = fixed_base(zk, "g1", [A, C])
-            expb = fixed_base(zk, "g2", [B])
-            ok &= proof[0:96] == exp[:96] and proof[432:528] == exp[96:] and proof[144:336] == expb
-    if rank == 0:
-        best = min(times)
-        print(json.dumps({"probe": "groth16_sharded", "n_gpus": world, "log_n": logn, "constraints": n,
-                          "prove_ms_best": best * 1e3, "prove_ms_all": [x * 1e3 for x in times],
-                          "proofs_per_s": 1.0 / best, "exact_ok": bool(ok),
-                          "timing": "wall clock around prove + gather + combine, max over ranks"}), flush=True)
-    _lib.check(zk.zk_key_free(h.value))
-    dom.free()
-    return ok
+    if not ok:
+        raise AssertionError("Groth16 proof differs from the closed form (2^%d, %s)" % (logn, circuit))
+    return rec
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--logn", type=int, nargs="*", default=[16])
     ap.add_argument("--iters", type=int, default=4)
+    ap.add_argument("--circuit", nargs="*", default=["mulchain"], choices=sorted(CIRCUITS))
     args = ap.parse_args()
-    ok = True
+    dist = None
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch
         import torch.distributed as dist
@@ -185,13 +220,10 @@ if __name__ == "__main__":
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", ""):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-        zk = _lib.lib()
-        for ln in args.logn:
-            ok &= run_sharded(zk, ln, args.iters)
+    zk = _lib.lib()
+    for ln in args.logn:
+        for c in args.circuit:
+            run(zk, ln, args.iters, c, dist)
+    if dist:
         dist.barrier()
         dist.destroy_process_group()
-    else:
-        zk = _lib.lib()
-        for ln in args.logn:
-            ok &= run(zk, ln, args.iters)
-    sys.exit(0 if ok else 1)

@@ -71,6 +71,7 @@ SIGNATURES = {
     "zk_groth16_pk_load": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64)]),
     "zk_groth16_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zk_groth16_prove_coeffs": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zk_groth16_last_device_ms": (c_int, [c_uint64, POINTER(ctypes.c_float)]),
     "zk_eval_domain_load": (c_int, [c_size_t, c_void_p, c_void_p, POINTER(c_uint64)]),
     "zk_r1cs_load": (c_int, [c_uint64, c_int, c_size_t, c_void_p, c_void_p, c_void_p]),
     "zk_groth16_prove_r1cs": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),

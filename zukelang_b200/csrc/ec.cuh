@@ -54,6 +54,15 @@ struct Fp2 {
     Fp t2 = fp_mul_outofline(a.c0 + a.c1, b.c0 + b.c1);
     return Fp2{t.lo - t.hi, t2 - t.lo - t.hi};
   }
+  // Two independent Fp2 products: their six Fp products go out as three interleaved pairs
+  // (Mont::mul2), so that every carry chain has an independent neighbour to overlap with.
+  static ZK_HD void mul2(const Fp2& a, const Fp2& b, const Fp2& c, const Fp2& d, Fp2& r1, Fp2& r2) {
+    FpPair p0 = fp_mul2_outofline(a.c0, b.c0, c.c0, d.c0);
+    FpPair p1 = fp_mul2_outofline(a.c1, b.c1, c.c1, d.c1);
+    FpPair pm = fp_mul2_outofline(a.c0 + a.c1, b.c0 + b.c1, c.c0 + c.c1, d.c0 + d.c1);
+    r1 = Fp2{p0.lo - p1.lo, pm.lo - p0.lo - p1.lo};
+    r2 = Fp2{p0.hi - p1.hi, pm.hi - p0.hi - p1.hi};
+  }
   // (c0 + c1 u)^2 = (c0 + c1)(c0 - c1) + 2 c0 c1 u : 2 Fp products
   ZK_HD Fp2 sqr() const {
     Fp s = c0 + c1;
@@ -86,6 +95,11 @@ struct FpCall {
   friend ZK_HD FpCall operator*(const FpCall& a, const FpCall& b) { return FpCall{a.f * b.f}; }
   ZK_HD FpCall sqr() const { return FpCall{f * f}; }
 #endif
+  static ZK_HD void mul2(const FpCall& a, const FpCall& b, const FpCall& c, const FpCall& d, FpCall& r1, FpCall& r2) {
+    FpPair p = fp_mul2_outofline(a.f, b.f, c.f, d.f);
+    r1.f = p.lo;
+    r2.f = p.hi;
+  }
   ZK_HD FpCall dbl() const { return FpCall{f.dbl()}; }
   ZK_HD FpCall neg() const { return FpCall{f.neg()}; }
   ZK_NI FpCall inverse() const { return FpCall{f.inverse()}; }
@@ -114,18 +128,24 @@ struct XYZZ {
   }
   ZK_HD XYZZ neg() const { return XYZZ{X, Y.neg(), ZZ, ZZZ}; }
 
+  // The out-of-line formulas below (latency-bound callers: bucket reduction, fix-ups, window
+  // combine, fixed-base ladders) issue their independent products as interleaved pairs (F::mul2):
+  // a lone warp then overlaps two carry chains instead of waiting on one.
+
   // 2 * (affine p)   — mdbl-2008-s-1
   static ZK_NI XYZZ dbl_affine(const Affine<F>& p) {
     if (p.is_inf() || p.y.is_zero()) return inf();
     F U = p.y.dbl();
     F V = U.sqr();
-    F W = U * V;
-    F S = p.x * V;
     F xx = p.x.sqr();
+    F W, S;
+    F::mul2(U, V, p.x, V, W, S);
     F M = xx.dbl() + xx;
     XYZZ r;
     r.X = M.sqr() - S.dbl();
-    r.Y = M * (S - r.X) - W * p.y;
+    F t1, t2;
+    F::mul2(M, S - r.X, W, p.y, t1, t2);
+    r.Y = t1 - t2;
     r.ZZ = V;
     r.ZZZ = W;
     return r;
@@ -136,19 +156,20 @@ struct XYZZ {
     if (is_inf() || Y.is_zero()) return inf();
     F U = Y.dbl();
     F V = U.sqr();
-    F W = U * V;
-    F S = X * V;
     F xx = X.sqr();
+    F W, S;
+    F::mul2(U, V, X, V, W, S);
     F M = xx.dbl() + xx;
     XYZZ r;
     r.X = M.sqr() - S.dbl();
-    r.Y = M * (S - r.X) - W * Y;
-    r.ZZ = V * ZZ;
-    r.ZZZ = W * ZZZ;
+    F t1, t2;
+    F::mul2(M, S - r.X, W, Y, t1, t2);
+    r.Y = t1 - t2;
+    F::mul2(V, ZZ, W, ZZZ, r.ZZ, r.ZZZ);
     return r;
   }
 
-  // madd with the independent products issued in interleaved pairs (Mont::mul2); Fp only
+  // madd with the independent products issued in interleaved pairs (F::mul2): what k_accumulate runs
   ZK_HD void madd_paired(const Affine<F>& p) {
     if (p.is_inf()) return;
     if (is_inf()) {
@@ -202,14 +223,13 @@ struct XYZZ {
     ZZZ = ZZZ * PPP;
   }
 
-  // this += q   — add-2008-s
+  // this += q   — add-2008-s, products in interleaved pairs (7 pair steps for 12M + 2S)
   ZK_NI void add(const XYZZ& q) {
     if (q.is_inf()) return;
     if (is_inf()) { *this = q; return; }
-    F U1 = X * q.ZZ;
-    F U2 = q.X * ZZ;
-    F S1 = Y * q.ZZZ;
-    F S2 = q.Y * ZZZ;
+    F U1, U2, S1, S2;
+    F::mul2(X, q.ZZ, q.X, ZZ, U1, U2);
+    F::mul2(Y, q.ZZZ, q.Y, ZZZ, S1, S2);
     F Pd = U2 - U1;
     F Rd = S2 - S1;
     if (Pd.is_zero()) {
@@ -218,13 +238,16 @@ struct XYZZ {
       return;
     }
     F PP = Pd.sqr();
-    F PPP = Pd * PP;
-    F Q = U1 * PP;
-    F X3 = Rd.sqr() - PPP - Q.dbl();
-    Y = Rd * (Q - X3) - S1 * PPP;
+    F RR = Rd.sqr();
+    F PPP, Q;
+    F::mul2(Pd, PP, U1, PP, PPP, Q);
+    F X3 = RR - PPP - Q.dbl();
+    F t1, t2, z2, z3;
+    F::mul2(Rd, Q - X3, S1, PPP, t1, t2);
+    F::mul2(ZZ, q.ZZ, ZZZ, q.ZZZ, z2, z3);
+    F::mul2(z2, PP, z3, PPP, ZZ, ZZZ);
+    Y = t1 - t2;
     X = X3;
-    ZZ = ZZ * q.ZZ * PP;
-    ZZZ = ZZZ * q.ZZZ * PPP;
   }
 
   // affine coordinates (one field inversion); identity -> (0, 0)

@@ -97,14 +97,12 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   tile_sums.alloc(cdiv(nb, SCAN_TILE) + 1);
   entries.alloc((size_t)n * cfg.W);
   {
-    // 9 (G1 default): paired products + cp.async staging, 2 blocks/SM; 8: paired, direct loads;
-    // 5 (G2 default): plain mixed add + staging; 4: plain, direct loads, 2 blocks/SM; 1: plain at 128
-    // registers, 4 blocks/SM
+    // 9 (default): mixed add with paired products + cp.async staging, 2 blocks/SM; 8: paired, direct
+    // loads; 5: plain mixed add + staging; 4: plain, direct loads, 2 blocks/SM; 1: plain, 4 blocks/SM
     constexpr bool is_g1 = sizeof(F) == sizeof(Fp);
-    acc_variant = env_int(is_g1 ? "ZKB200_ACC_VARIANT" : "ZKB200_ACC_VARIANT_G2", is_g1 ? ZK_ACC_VARIANT_DEFAULT : 5);
-    if (!is_g1 && acc_variant >= 8) acc_variant -= 4;
+    acc_variant = env_int(is_g1 ? "ZKB200_ACC_VARIANT" : "ZKB200_ACC_VARIANT_G2", ZK_ACC_VARIANT_DEFAULT);
     if (acc_variant != 1 && acc_variant != 4 && acc_variant != 5 && acc_variant != 8 && acc_variant != 9)
-      acc_variant = is_g1 ? ZK_ACC_VARIANT_DEFAULT : 5;
+      acc_variant = ZK_ACC_VARIANT_DEFAULT;
     int per_sm = acc_occupancy();
     if (per_sm < 1) per_sm = 1;
     acc_blocks = (uint32_t)per_sm * (uint32_t)sm_count();
@@ -164,11 +162,8 @@ void BaseTable<T>::acc_dispatch(Fn&& fn) {
     case 1: fn(k_accumulate<F, 4, false, false>, (size_t)0); break;
     case 4: fn(k_accumulate<F, 2, false, false>, (size_t)0); break;
     case 5: fn(k_accumulate<F, 2, true, false>, SM); break;
-    case 8:
-      if constexpr (sizeof(F) == sizeof(Fp)) fn(k_accumulate<F, 2, false, true>, (size_t)0);
-      break;
-    default:
-      if constexpr (sizeof(F) == sizeof(Fp)) fn(k_accumulate<F, 2, true, true>, SM);
+    case 8: fn(k_accumulate<F, 2, false, true>, (size_t)0); break;
+    default: fn(k_accumulate<F, 2, true, true>, SM);
   }
 }
 template <class T>

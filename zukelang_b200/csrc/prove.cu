@@ -85,8 +85,13 @@ struct Groth16Key : HandleBase {
   DevBuf<XYZZ<Fp2>> g2;     // [part]
   DevBuf<uint8_t> d_out;
   cudaEvent_t ready = nullptr;
+  cudaEvent_t t_begin = nullptr, t_end = nullptr;   // device time of the last prove (zk_groth16_last_device_ms)
   Groth16Key() { kind = 4; }
-  ~Groth16Key() { if (ready) cudaEventDestroy(ready); }
+  ~Groth16Key() {
+    if (ready) cudaEventDestroy(ready);
+    if (t_begin) cudaEventDestroy(t_begin);
+    if (t_end) cudaEventDestroy(t_end);
+  }
 };
 
 static __global__ void __launch_bounds__(128)
@@ -175,6 +180,8 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
   k->g2.alloc(nparts);
   k->d_out.alloc(ZK_GROTH16_PROOF_OUT);
   ZK_CUDA(cudaEventCreateWithFlags(&k->ready, cudaEventDisableTiming));
+  ZK_CUDA(cudaEventCreate(&k->t_begin));
+  ZK_CUDA(cudaEventCreate(&k->t_end));
   *handle = register_handle(std::move(k));
   ZK_API_END
 }
@@ -221,6 +228,7 @@ static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* 
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_GROTH16_PROOF_OUT, cudaMemcpyDeviceToHost, st0));
   ZK_CUDA(cudaMemcpyAsync(fl, flag, sizeof(fl), cudaMemcpyDeviceToHost, st0));
+  ZK_CUDA(cudaEventRecord(k->t_end, st0));
   ZK_CUDA(cudaStreamSynchronize(st0));
   ZK_REQUIRE(fl[0] == 0, ZK_EPOINT, "groth16_prove: scalar is not canonical (>= r)");
   ZK_REQUIRE(fl[1] == 0, ZK_EREMAINDER, "groth16_prove: V*W - Y is not divisible by the target (QAP.ml:134)");
@@ -250,6 +258,7 @@ int zk_groth16_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* sol
   ZK_REQUIRE(q.n == k->n && q.m == k->m, ZK_EARG, "groth16_prove: key and QAP dimensions differ");
   check_rs(r, s);
   cudaStream_t st = default_stream();
+  ZK_CUDA(cudaEventRecord(k->t_begin, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
@@ -271,6 +280,7 @@ int zk_groth16_prove_coeffs(uint64_t pk_handle, uint64_t qap_handle, const uint8
   ZK_REQUIRE(q.n == k->n, ZK_EARG, "groth16_prove_coeffs: key and domain dimensions differ");
   check_rs(r, s);
   cudaStream_t st = default_stream();
+  ZK_CUDA(cudaEventRecord(k->t_begin, st));
   qh->d_raw.ensure(3 * (size_t)q.n * 8);
   ZK_CUDA(cudaMemcpyAsync(qh->d_raw.p, vwy, 3 * (size_t)q.n * 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
@@ -296,11 +306,24 @@ int zk_groth16_prove_r1cs(uint64_t pk_handle, uint64_t domain_handle, const uint
   ZK_REQUIRE(d.n == k->n && d.m == k->m, ZK_EARG, "groth16_prove_r1cs: key and domain dimensions differ");
   check_rs(r, s);
   cudaStream_t st = default_stream();
+  ZK_CUDA(cudaEventRecord(k->t_begin, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
   d.eval(k->d_sol.p, st);
   groth16_finish(k, d.evals.p, d.H.p, d.flag.p, st, proof_out);
+  ZK_API_END
+}
+
+// Device time of the last zk_groth16_prove* on this key: from the first upload to the last
+// download, CUDA events on the primary device's stream (the other devices' work is inside: the
+// primary stream waits for it before the combine).
+int zk_groth16_last_device_ms(uint64_t pk_handle, float* ms) {
+  ZK_API_BEGIN
+  using namespace zk;
+  auto* k = static_cast<Groth16Key*>(lookup_handle(pk_handle, 4));
+  ZK_REQUIRE(ms, ZK_EARG, "groth16_last_device_ms: null argument");
+  ZK_CUDA(cudaEventElapsedTime(ms, k->t_begin, k->t_end));
   ZK_API_END
 }
 
