@@ -18,10 +18,13 @@ static void zk_raise(int rc) {
   if (rc == ZK_EARG) caml_invalid_argument(zk_last_error());   /* curve.ml:116 Invalid_argument */
   caml_failwith(zk_last_error());                              /* assert false / assert (is_zero rem) */
 }
+/* an argument error found by the stub itself: zk_last_error() would be a stale library message */
+static void zk_raise_arg(const char *msg) { caml_invalid_argument(msg); }
 
 static uint8_t *dup_bytes(value v, size_t *len) {
   size_t n = caml_string_length(v);
   uint8_t *p = (uint8_t *)malloc(n ? n : 1);
+  if (!p) caml_failwith("zkb200: out of memory copying an argument");
   memcpy(p, Bytes_val(v), n);
   if (len) *len = n;
   return p;
@@ -34,6 +37,68 @@ CAMLprim value zkb200_init(value dev) {
   CAMLreturn(Val_unit);
 }
 
+/* init_devices : int array -> unit.  One process drives the listed GPUs of the box; keys and tables
+ * loaded afterwards spread over them and prove returns the finished proof (protocol.mli:23). */
+CAMLprim value zkb200_init_devices(value devs) {
+  CAMLparam1(devs);
+  int d[8];
+  size_t n = Wosize_val(devs);
+  if (n < 1 || n > 8) zk_raise_arg("zkb200_init_devices: 1 to 8 devices expected");
+  for (size_t i = 0; i < n; i++) d[i] = Int_val(Field(devs, i));
+  int rc = zk_init_devices(d, (int)n);
+  if (rc) zk_raise(rc);
+  CAMLreturn(Val_unit);
+}
+
+/* ---- resident base tables: a key field uploaded once, many MSMs against it -------------------
+ * table_load : g2:bool -> bases:bytes -> precompute:bool -> int64;  table_msm : g2:bool -> int64 ->
+ * scalars:bytes -> bytes;  table_free : int64 -> unit.  Behind Curve.G.dot / apply_powers
+ * (curve.ml:94-118) when the same point list is used again (ocaml/zkb200.ml: Resident). */
+CAMLprim value zkb200_table_load(value g2, value bases, value precompute) {
+  CAMLparam3(g2, bases, precompute);
+  size_t nb;
+  const int is2 = Int_val(g2) != 0, pre = Int_val(precompute) != 0;
+  const size_t raw = is2 ? ZK_G2_RAW : ZK_G1_RAW;
+  uint8_t *b = dup_bytes(bases, &nb);
+  uint64_t h = 0;
+  int rc = 0;
+  if (nb == 0 || nb % raw) { free(b); zk_raise_arg("zkb200_table_load: bases must be a non-empty multiple of the point size"); }
+  caml_release_runtime_system();
+  rc = is2 ? zk_g2_table_load(b, NULL, nb / raw, pre, 0, &h) : zk_g1_table_load(b, NULL, nb / raw, pre, 0, &h);
+  caml_acquire_runtime_system();
+  free(b);
+  if (rc) zk_raise(rc);
+  CAMLreturn(caml_copy_int64((int64_t)h));
+}
+
+CAMLprim value zkb200_table_msm(value g2, value handle, value scalars) {
+  CAMLparam3(g2, handle, scalars);
+  CAMLlocal1(out);
+  size_t ns;
+  const int is2 = Int_val(g2) != 0;
+  const size_t outn = is2 ? ZK_G2_OUT : ZK_G1_OUT;
+  uint8_t *s = dup_bytes(scalars, &ns);
+  uint8_t res[ZK_G2_OUT];
+  uint64_t h = (uint64_t)Int64_val(handle);
+  int rc = 0;
+  if (ns == 0 || ns % ZK_FR_BYTES) { free(s); zk_raise_arg("zkb200_table_msm: scalars must be a non-empty multiple of 32 bytes"); }
+  caml_release_runtime_system();
+  rc = is2 ? zk_g2_table_msm(h, s, ns / ZK_FR_BYTES, res) : zk_g1_table_msm(h, s, ns / ZK_FR_BYTES, res);
+  caml_acquire_runtime_system();
+  free(s);
+  if (rc) zk_raise(rc);
+  out = caml_alloc_string(outn);
+  memcpy(Bytes_val(out), res, outn);
+  CAMLreturn(out);
+}
+
+CAMLprim value zkb200_table_free(value h) {
+  CAMLparam1(h);
+  int rc = zk_table_free((uint64_t)Int64_val(h));
+  if (rc) zk_raise(rc);
+  CAMLreturn(Val_unit);
+}
+
 /* g1_msm : bases:bytes (96 n) -> scalars:bytes (32 n) -> bytes (144)   — Curve.G.dot / apply_powers */
 CAMLprim value zkb200_g1_msm(value bases, value scalars) {
   CAMLparam2(bases, scalars);
@@ -42,12 +107,11 @@ CAMLprim value zkb200_g1_msm(value bases, value scalars) {
   uint8_t *b = dup_bytes(bases, &nb), *s = dup_bytes(scalars, &ns);
   uint8_t res[ZK_G1_OUT];
   size_t n = ns / ZK_FR_BYTES;
-  int rc = (nb == n * ZK_G1_RAW) ? 0 : ZK_EARG;
-  if (!rc) {
-    caml_release_runtime_system();
-    rc = zk_g1_msm(b, NULL, s, n, res);
-    caml_acquire_runtime_system();
-  }
+  int rc = 0;
+  if (nb != n * ZK_G1_RAW || ns % ZK_FR_BYTES) { free(b); free(s); zk_raise_arg("zkb200_g1_msm: 96 bytes per base and 32 per scalar expected"); }
+  caml_release_runtime_system();
+  rc = zk_g1_msm(b, NULL, s, n, res);
+  caml_acquire_runtime_system();
   free(b); free(s);
   if (rc) zk_raise(rc);
   out = caml_alloc_string(ZK_G1_OUT);
@@ -62,12 +126,11 @@ CAMLprim value zkb200_g2_msm(value bases, value scalars) {
   uint8_t *b = dup_bytes(bases, &nb), *s = dup_bytes(scalars, &ns);
   uint8_t res[ZK_G2_OUT];
   size_t n = ns / ZK_FR_BYTES;
-  int rc = (nb == n * ZK_G2_RAW) ? 0 : ZK_EARG;
-  if (!rc) {
-    caml_release_runtime_system();
-    rc = zk_g2_msm(b, NULL, s, n, res);
-    caml_acquire_runtime_system();
-  }
+  int rc = 0;
+  if (nb != n * ZK_G2_RAW || ns % ZK_FR_BYTES) { free(b); free(s); zk_raise_arg("zkb200_g2_msm: 192 bytes per base and 32 per scalar expected"); }
+  caml_release_runtime_system();
+  rc = zk_g2_msm(b, NULL, s, n, res);
+  caml_acquire_runtime_system();
   free(b); free(s);
   if (rc) zk_raise(rc);
   out = caml_alloc_string(ZK_G2_OUT);
@@ -251,12 +314,14 @@ CAMLprim value zkb200_pairing_product(value g1, value g2, value neg) {
   uint8_t *f = dup_bytes(neg, &nn);
   size_t n = n1 / ZK_G1_RAW;
   uint8_t res[ZK_GT_BYTES];
-  int rc = ZK_EARG;
-  if (n1 % ZK_G1_RAW == 0 && n2 == n * ZK_G2_RAW && (nn == 0 || nn == n)) {
-    caml_release_runtime_system();
-    rc = zk_pairing_product(a, b, nn ? f : NULL, n, res);
-    caml_acquire_runtime_system();
+  int rc = 0;
+  if (n1 % ZK_G1_RAW || n2 != n * ZK_G2_RAW || (nn != 0 && nn != n)) {
+    free(a); free(b); free(f);
+    zk_raise_arg("zkb200_pairing_product: n G1 points, n G2 points and 0 or n flags expected");
   }
+  caml_release_runtime_system();
+  rc = zk_pairing_product(a, b, nn ? f : NULL, n, res);
+  caml_acquire_runtime_system();
   free(a); free(b); free(f);
   if (rc) zk_raise(rc);
   out = caml_alloc_string(ZK_GT_BYTES);
@@ -272,12 +337,11 @@ CAMLprim value zkb200_gt_mul(value x, value y) {
   uint8_t *a = dup_bytes(x, &nx);
   uint8_t *b = dup_bytes(y, &ny);
   uint8_t res[ZK_GT_BYTES];
-  int rc = ZK_EARG;
-  if (nx == ZK_GT_BYTES && ny == ZK_GT_BYTES) {
-    caml_release_runtime_system();
-    rc = zk_gt_mul(a, b, res);
-    caml_acquire_runtime_system();
-  }
+  int rc = 0;
+  if (nx != ZK_GT_BYTES || ny != ZK_GT_BYTES) { free(a); free(b); zk_raise_arg("zkb200_gt_mul: two 576-byte GT values expected"); }
+  caml_release_runtime_system();
+  rc = zk_gt_mul(a, b, res);
+  caml_acquire_runtime_system();
   free(a); free(b);
   if (rc) zk_raise(rc);
   out = caml_alloc_string(ZK_GT_BYTES);
@@ -295,12 +359,12 @@ static value decompress_stub(value comp, int g2) {
   uint8_t *in = dup_bytes(comp, &nb);
   size_t n = nb / cb;
   uint8_t *res = (uint8_t *)malloc(n * rb + 1);
-  int rc = ZK_EARG;
-  if (res && nb % cb == 0 && n > 0) {
-    caml_release_runtime_system();
-    rc = g2 ? zk_g2_decompress(in, n, res) : zk_g1_decompress(in, n, res);
-    caml_acquire_runtime_system();
-  }
+  int rc = 0;
+  if (!res) { free(in); caml_failwith("zkb200: out of memory"); }
+  if (nb % cb || n == 0) { free(in); free(res); zk_raise_arg("zkb200_decompress: a non-empty multiple of the compressed point size expected"); }
+  caml_release_runtime_system();
+  rc = g2 ? zk_g2_decompress(in, n, res) : zk_g1_decompress(in, n, res);
+  caml_acquire_runtime_system();
   free(in);
   if (rc) { free(res); zk_raise(rc); }
   out = caml_alloc_string(n * rb);

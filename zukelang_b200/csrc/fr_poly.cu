@@ -116,11 +116,119 @@ void NttPlan::build(int logD_, cudaStream_t st) {
   ZK_CUDA(cudaStreamSynchronize(st));  // consts is freed on return
 }
 
+// ---------------------------------------------------------------------------
+// fused passes: K consecutive radix-2 stages per launch, on a tile staged in shared memory
+// ---------------------------------------------------------------------------
+// A radix-2 stage moves 64 B per butterfly through HBM for one Fr product: at 2^21 points a stage is
+// HBM-bound (and a launch each).  A pass keeps a tile of 2^TL elements in shared memory and runs K
+// stages on it, so the data crosses HBM once per pass (3 passes instead of 21 stages at 2^21); what
+// is left is the integer pipe (one Fr product per butterfly).
+//
+// Index bits of a pass over stages [s0, s0 + K): i = hi (s0 bits) | m (K bits) | low (L bits), stage
+// s0 + t pairs m with m ^ 2^(K-1-t).  A tile holds every m for C = 2^(TL-K) consecutive values of
+// `low` (C * 32 contiguous bytes per m), element (m, c) at slot m * C + c.  The two 16-byte halves of
+// an element live in separate planes, so consecutive threads touch consecutive 16-byte words.
+constexpr int NTT_TL = 10;                   // tile = 1024 elements = 32 KB
+constexpr int NTT_THREADS = 256;
+struct NttPass {
+  int s0, K, logC;                           // first stage, stages, log2(C)
+};
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(NTT_THREADS)
+k_ntt_pass(Fr* __restrict__ x, const Fr* __restrict__ tw, uint32_t D, int logD, NttPass P) {
+  extern __shared__ uint4 ntt_tile[];        // [2][tile]
+  const int K = P.K, logC = P.logC;
+  const uint32_t tile = 1u << (K + logC), C = 1u << logC;
+  const int L = logD - P.s0 - K;             // low bits below the K stage bits
+  Fr* v = x + (size_t)blockIdx.y * D;
+  // tile id -> (hi, low base): tiles per hi block = 2^L / C
+  const uint32_t tiles_per_hi = 1u << (L - logC);
+  const uint32_t hi = blockIdx.x / tiles_per_hi, lowbase = (blockIdx.x % tiles_per_hi) << logC;
+  const size_t base = ((size_t)hi << (logD - P.s0)) + lowbase;
+  auto gidx = [&](uint32_t e) { return base + ((size_t)(e >> logC) << L) + (e & (C - 1)); };
+  for (uint32_t e = threadIdx.x; e < tile; e += NTT_THREADS) {
+    const uint4* src = reinterpret_cast<const uint4*>(&v[gidx(e)]);
+    ntt_tile[e] = src[0];
+    ntt_tile[tile + e] = src[1];
+  }
+  __syncthreads();
+  for (int tt = 0; tt < K; tt++) {
+    const int t = INVERSE ? K - 1 - tt : tt; // inverse: smallest distance first
+    const int s = P.s0 + t;                  // global stage: pairs at distance D >> (s + 1)
+    const int pb = K - 1 - t;                // bit of m that differs inside a pair
+    for (uint32_t q = threadIdx.x; q < tile / 2; q += NTT_THREADS) {
+      const uint32_t c = q & (C - 1), mm = q >> logC;
+      const uint32_t m0 = ((mm >> pb) << (pb + 1)) | (mm & ((1u << pb) - 1));
+      const uint32_t e0 = (m0 << logC) | c, e1 = e0 + (1u << (pb + logC));
+      // twiddle exponent: (i0 mod half) << s, i0 mod half = (m0 mod 2^pb) << L | low
+      const uint32_t j = ((m0 & ((1u << pb) - 1)) << L) | (lowbase + c);
+      Fr a, b;
+      uint4* a4 = reinterpret_cast<uint4*>(&a);
+      uint4* b4 = reinterpret_cast<uint4*>(&b);
+      a4[0] = ntt_tile[e0]; a4[1] = ntt_tile[tile + e0];
+      b4[0] = ntt_tile[e1]; b4[1] = ntt_tile[tile + e1];
+      const Fr w = load_vec(&tw[(size_t)j << s]);
+      Fr r0, r1;
+      if (INVERSE) { b = b * w; r0 = a + b; r1 = a - b; }
+      else { r0 = a + b; r1 = (a - b) * w; }
+      const uint4* r04 = reinterpret_cast<const uint4*>(&r0);
+      const uint4* r14 = reinterpret_cast<const uint4*>(&r1);
+      ntt_tile[e0] = r04[0]; ntt_tile[tile + e0] = r04[1];
+      ntt_tile[e1] = r14[0]; ntt_tile[tile + e1] = r14[1];
+    }
+    __syncthreads();
+  }
+  for (uint32_t e = threadIdx.x; e < tile; e += NTT_THREADS) {
+    uint4* dst = reinterpret_cast<uint4*>(&v[gidx(e)]);
+    dst[0] = ntt_tile[e];
+    dst[1] = ntt_tile[tile + e];
+  }
+}
+
+// Passes of a transform of 2^logD points, in forward (DIF) stage order: the last pass takes the
+// final min(TL, logD) stages on contiguous tiles (C = 1 group each); the stages before it are split
+// evenly into passes of at most TL - 3 stages (C >= 8: 256-byte contiguous runs).
+static int ntt_plan_passes(int logD, NttPass out[8]) {
+  int np = 0;
+  const int klast = logD < NTT_TL ? logD : NTT_TL;
+  const int rest = logD - klast;
+  if (rest > 0) {
+    const int km = NTT_TL - 3;
+    const int cnt = (rest + km - 1) / km;
+    int s0 = 0;
+    for (int i = 0; i < cnt; i++) {
+      int K = rest / cnt + (i < rest % cnt ? 1 : 0);
+      out[np++] = NttPass{s0, K, NTT_TL - K};
+      s0 += K;
+    }
+  }
+  out[np++] = NttPass{rest, klast, 0};
+  return np;
+}
+
+static void ntt_launch(const NttPlan& p, Fr* d, int batch, bool inverse, cudaStream_t st) {
+  NttPass passes[8];
+  const int np = ntt_plan_passes(p.logD, passes);
+  for (int i = 0; i < np; i++) {
+    const NttPass& P = passes[inverse ? np - 1 - i : i];
+    const uint32_t tile = 1u << (P.K + P.logC);
+    dim3 grid(p.D / tile, batch);
+    const size_t smem = 2 * (size_t)tile * sizeof(uint4);
+    if (inverse) k_ntt_pass<true><<<grid, NTT_THREADS, smem, st>>>(d, p.tw_inv.p, p.D, p.logD, P);
+    else k_ntt_pass<false><<<grid, NTT_THREADS, smem, st>>>(d, p.tw.p, p.D, p.logD, P);
+  }
+}
+
+static bool ntt_fused() { static int f = env_int("ZKB200_NTT_FUSED", 1); return f != 0; }
+
 static void ntt_forward_batch(const NttPlan& p, Fr* d, int batch, cudaStream_t st) {
+  if (ntt_fused()) return ntt_launch(p, d, batch, false, st);
   dim3 grid(cdiv(p.D / 2, 256), batch);
   for (int s = 0; s < p.logD; s++) k_ntt_dif_stage<<<grid, 256, 0, st>>>(d, p.tw.p, p.D, p.logD - 1 - s, s);
 }
 static void ntt_inverse_batch(const NttPlan& p, Fr* d, int batch, cudaStream_t st) {
+  if (ntt_fused()) return ntt_launch(p, d, batch, true, st);
   dim3 grid(cdiv(p.D / 2, 256), batch);
   for (int s = p.logD - 1; s >= 0; s--) k_ntt_dit_stage<<<grid, 256, 0, st>>>(d, p.tw_inv.p, p.D, p.logD - 1 - s, s);
 }
@@ -203,14 +311,15 @@ static __global__ void k_quotient_pointwise(const Fr* __restrict__ work, uint32_
   Fr v = load_vec_rw(&work[j]), w = load_vec_rw(&work[(size_t)D + j]), y = load_vec_rw(&work[2 * (size_t)D + j]);
   store_vec(&H[j], (v * w - y) * load_vec(&t_inv[j]));
 }
-static __global__ void k_fr_mul_inplace(Fr* __restrict__ x, const Fr* __restrict__ y, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  store_vec(&x[i], load_vec_rw(&x[i]) * load_vec(&y[i]));
-}
 
-// Divisibility check (QAP.ml:134 `assert (is_zero rem)`): evaluate V, W, Y, t and h at a fixed
-// point x0 outside the coset and compare h(x0) t(x0) with V(x0) W(x0) - Y(x0).
+// Divisibility check (QAP.ml:134 `assert (is_zero rem)`).  h is interpolated from D >= n + 1 values of
+// (V W - Y) / t on the coset and truncated to n - 1 coefficients, so two things are verified:
+//  (1) the discarded coefficients n-1 .. D-1 are all zero (k_h_unshift_check) — exact;
+//  (2) h(x) t(x) = V(x) W(x) - Y(x) at TWO points off the coset: a fixed x0, and x1 derived from
+//      the values of all five polynomials at x0, so the second point depends on the witness and
+//      cannot be aimed at in advance.  Both sides have degree <= 2n - 2: a non-divisible input
+//      passes with probability <= (2n / r)^2 — the check is probabilistic, and DESIGN.md says so.
+// The evaluation-form prover's check (k_eval_prepare: V(j) W(j) = Y(j) on every domain point) is exact.
 struct EvalJob {
   const Fr* coeffs[5];
   uint32_t len[5];
@@ -223,8 +332,13 @@ static __device__ __forceinline__ Fr eval_point() {
   for (int i = 0; i < 8; i++) x.v[i] = c[i];
   return x;
 }
+// xs[0] = x0 (fixed)
+static __global__ void k_eval_point_init(Fr* xs) {
+  if (threadIdx.x || blockIdx.x) return;
+  xs[0] = eval_point();
+}
 static __global__ void __launch_bounds__(EVAL_THREADS)
-k_poly_eval_partial(EvalJob job, Fr* __restrict__ partials, uint32_t blocks_per_poly) {
+k_poly_eval_partial(EvalJob job, const Fr* __restrict__ xp, Fr* __restrict__ partials, uint32_t blocks_per_poly) {
   __shared__ Fr sm[EVAL_THREADS];
   int which = blockIdx.y;
   const Fr* c = job.coeffs[which];
@@ -233,7 +347,7 @@ k_poly_eval_partial(EvalJob job, Fr* __restrict__ partials, uint32_t blocks_per_
   uint32_t i0 = t * EVAL_CHUNK;
   Fr acc = Fr::zero();
   if (i0 < n) {
-    Fr x0 = eval_point();
+    Fr x0 = load_vec_rw(xp);
     uint32_t end = min(n, i0 + EVAL_CHUNK);
     for (int i = (int)end - 1; i >= (int)i0; i--) acc = acc * x0 + load_vec_rw(&c[i]);
     acc = acc * fr_pow_u32(x0, i0);
@@ -246,7 +360,10 @@ k_poly_eval_partial(EvalJob job, Fr* __restrict__ partials, uint32_t blocks_per_
   }
   if (threadIdx.x == 0) partials[(size_t)which * blocks_per_poly + blockIdx.x] = sm[0];
 }
-static __global__ void k_poly_eval_check(const Fr* __restrict__ partials, uint32_t blocks_per_poly, int* flag) {
+// Compares the two sides at the point just evaluated; next (nullable) receives the following point:
+// x0 + sum_w e_w x0^(w+1), a polynomial mix of the five values.
+static __global__ void k_poly_eval_check(const Fr* __restrict__ partials, uint32_t blocks_per_poly, const Fr* xp, Fr* next,
+                                         int* flag) {
   if (threadIdx.x || blockIdx.x) return;
   Fr e[5];
   for (int w = 0; w < 5; w++) {
@@ -256,6 +373,23 @@ static __global__ void k_poly_eval_check(const Fr* __restrict__ partials, uint32
   }
   // order: V, W, Y, t, h
   if (e[4] * e[3] != e[0] * e[1] - e[2]) atomicExch(flag, 1);
+  if (next) {
+    Fr x = load_vec_rw(xp), mix = x, pw = x;
+    for (int w = 0; w < 5; w++) { mix = mix + e[w] * pw; pw = pw * x; }
+    *next = mix;
+  }
+}
+// H <- H .* coset_inv (undo the coset shift); coefficients n - 1 .. D - 1 must vanish
+static __global__ void k_h_unshift_check(Fr* __restrict__ H, const Fr* __restrict__ coset_inv, uint32_t D, uint32_t keep,
+                                         int* flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  Fr h = load_vec_rw(&H[i]);
+  if (i >= keep) {
+    if (!h.is_zero()) atomicExch(flag, 1);
+    return;
+  }
+  store_vec(&H[i], h * load_vec(&coset_inv[i]));
 }
 
 // ---------------------------------------------------------------------------
@@ -456,6 +590,7 @@ void QapDevice::load(const uint8_t* v, const uint8_t* w, const uint8_t* y, const
   Vc.alloc(3 * (size_t)n);      // coefficient copies: V | W | Y, n each
   uint32_t bpp = cdiv(cdiv(n + 1, EVAL_CHUNK), EVAL_THREADS);
   partials.alloc(5 * (size_t)bpp);
+  eval_xs.alloc(2);
   ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
 }
 
@@ -473,8 +608,8 @@ void QapDevice::quotient_from_work(cudaStream_t st) {
   ntt_forward_batch(plan, V.p, 3, st);
   k_quotient_pointwise<<<cdiv(D, 256), 256, 0, st>>>(V.p, D, t_inv_evals.p, H.p);
   plan.inverse(H.p, st);
-  k_fr_mul_inplace<<<cdiv(D, 256), 256, 0, st>>>(H.p, plan.coset_inv.p, D);
-  // divisibility check at x0
+  k_h_unshift_check<<<cdiv(D, 256), 256, 0, st>>>(H.p, plan.coset_inv.p, D, n > 0 ? n - 1 : 0, flag.p + 1);
+  // divisibility check at x0 and at a witness-dependent x1
   EvalJob job;
   job.coeffs[0] = Vc.p; job.len[0] = n;
   job.coeffs[1] = Vc.p + n; job.len[1] = n;
@@ -482,8 +617,11 @@ void QapDevice::quotient_from_work(cudaStream_t st) {
   job.coeffs[3] = target.p; job.len[3] = n + 1;
   job.coeffs[4] = H.p; job.len[4] = n > 0 ? n - 1 : 0;
   uint32_t bpp = cdiv(cdiv(n + 1, EVAL_CHUNK), EVAL_THREADS);
-  k_poly_eval_partial<<<dim3(bpp, 5), EVAL_THREADS, 0, st>>>(job, partials.p, bpp);
-  k_poly_eval_check<<<1, 1, 0, st>>>(partials.p, bpp, flag.p + 1);
+  k_eval_point_init<<<1, 1, 0, st>>>(eval_xs.p);
+  for (int round = 0; round < 2; round++) {
+    k_poly_eval_partial<<<dim3(bpp, 5), EVAL_THREADS, 0, st>>>(job, eval_xs.p + round, partials.p, bpp);
+    k_poly_eval_check<<<1, 1, 0, st>>>(partials.p, bpp, eval_xs.p + round, round == 0 ? eval_xs.p + 1 : nullptr, flag.p + 1);
+  }
   ZK_CUDA(cudaGetLastError());
 }
 

@@ -42,6 +42,7 @@ struct QapDevice {
   DevBuf<Fr> Vc;                  // coefficients V | W | Y, n each (the A / B / B1 MSM scalars)
   DevBuf<Fr> H;                   // quotient coefficients (n - 1 used), Montgomery
   DevBuf<Fr> partials;
+  DevBuf<Fr> eval_xs;     // the two evaluation points of the divisibility check
   DevBuf<int> flag;               // [0] non-canonical input, [1] remainder != 0
   void load(const uint8_t* v, const uint8_t* w, const uint8_t* y, const uint8_t* target, uint32_t m, uint32_t n,
             cudaStream_t st);

@@ -15,6 +15,7 @@
 namespace zk {
 
 constexpr int MAX_DEVICES = 8;
+int env_int(const char* name, int dflt);  // integer environment knob (runtime.cu)
 
 struct HandleBase {
   int kind = 0;  // 1 = G1 table, 2 = G2 table, 3 = QAP, 4 = Groth16 key, 5 = Pinocchio key, 6 = evaluation domain
