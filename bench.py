@@ -286,7 +286,7 @@ def run_gpu_arm(args):
         tot = sum(a * d for a, d in zip(ints, dl_all)) % R
         host = torch.from_numpy(np.ascontiguousarray(w[lo:hi]).view(np.int64)).pin_memory()
         batches.append({"host": host, "dev": host.cuda(), "expect_dlog": tot})
-    QUEUE = 16                                          # zk_table_pipeline batches up to 16 tails
+    QUEUE = int(os.environ.get("ZKB200_BENCH_QUEUE", "32"))   # zk_table_pipeline batches up to 32 tails per join
     d_ring = torch.zeros(QUEUE, 144, dtype=torch.uint8, device="cuda")    # one result slot per queued MSM
     p_ring = torch.zeros(QUEUE, 96, dtype=torch.uint8, device="cuda")     # partial sums to gather (N > 1)
     g_ring = torch.zeros(world, QUEUE, 96, dtype=torch.uint8, device="cuda")
@@ -296,9 +296,10 @@ def run_gpu_arm(args):
 
     def run_steps(batch_ids):
         """One MSM per entry of batch_ids, device-resident scalars, on stream `side`.
-        Pipelined: groups of up to 16 MSMs sort + accumulate back to back, then ONE batched tail
-        (zk_table_join) finishes the group; for N > 1 the group's partial sums travel in one
-        all_gather and are added by one batched kernel.  Returns the last result tensor."""
+        Pipelined: up to QUEUE MSMs are queued and zk_table_join runs the group as ONE launch
+        sequence (one counting sort and one balanced accumulation over all their buckets, one batched
+        tail); for N > 1 the group's partial sums travel in one all_gather and are added by one
+        batched kernel.  Returns the last result tensor."""
         group = QUEUE if pipelined else 1
         last = None
         for g0 in range(0, len(batch_ids), group):
@@ -337,7 +338,7 @@ def run_gpu_arm(args):
     peak_mac32 = peak_imad / 2.0                       # one MAC32 = mad.lo + mad.hi
 
     # ---- warm-up, with the exact known-dlog check -------------------------------------------
-    _lib.check(zk.zk_table_pipeline(handle.value, 1 if pipelined else 0))
+    _lib.check(zk.zk_table_pipeline(handle.value, QUEUE if pipelined else 0))
     with torch.cuda.stream(side):
         for it in range(args.warmup):
             b = it % pool
@@ -348,6 +349,7 @@ def run_gpu_arm(args):
     # ---- timed region: `value` (inputs resident in HBM) -----------------------------------------
     stage = (ctypes.c_float * 4)()
     slots = [(args.warmup + it) % pool for it in range(args.steps)]   # scalar batch of every step
+    _lib.check(zk.zk_table_profile(handle.value, 1, None))            # stage events around every join (5 records each)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_region0 = time.time()
@@ -360,7 +362,14 @@ def run_gpu_arm(args):
     dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop(t_region0, t_region1)
     assert combine(res) == expected_point(batches[slots[-1]]["expect_dlog"])
-    # stage times of the dominant kernel: a few more steps, one at a time, with stage events on
+    # the dominant kernel INSIDE the timed region: summed launch durations of k_accumulate (CUDA events
+    # on the launching stream) and the MSMs those launches processed
+    totals, counts = (ctypes.c_float * 4)(), (ctypes.c_uint64 * 2)()
+    _lib.check(zk.zk_table_profile_totals(handle.value, totals, counts))
+    _lib.check(zk.zk_table_profile(handle.value, 0, None))
+    timed_stage_ms = [float(x) for x in totals]
+    timed_msms, timed_joins = int(counts[0]), int(counts[1])
+    # stage times of one step on its own (single-MSM launches), for reference
     acc_ms, stages_last = [], None
     _lib.check(zk.zk_table_profile(handle.value, 1, None))
     with torch.cuda.stream(side):
@@ -431,10 +440,13 @@ def run_gpu_arm(args):
     e2e_split = None
     if tm:
         med = lambda xs: sorted(xs)[len(xs) // 2]
+        groups = sorted({(x[2], x[3]) for x in tm})                 # kernel window of every group of steps
+        sizes = [sum(1 for x in tm if (x[2], x[3]) == g) for g in groups]
         e2e_split = {"steps_timed": len(tm), "h2d_ms_per_step_median": med([x[1] - x[0] for x in tm]),
-                     "compute_ms_per_step_median": med([x[3] - x[2] for x in tm]),
-                     "compute_stream_stall_ms_total": sum(max(0.0, tm[i][2] - tm[i - 1][3]) for i in range(1, len(tm))),
-                     "first_kernel_after_ms": tm[0][2], "last_kernel_done_ms": tm[-1][3]}
+                     "groups": [{"steps": k, "kernels_start_ms": g[0], "kernels_ms": g[1] - g[0]} for g, k in zip(groups, sizes)],
+                     "compute_ms_per_step": sum(g[1] - g[0] for g in groups) / len(tm),
+                     "compute_stream_stall_ms_total": groups[0][0] + sum(max(0.0, groups[i][0] - groups[i - 1][1]) for i in range(1, len(groups))),
+                     "first_kernel_after_ms": groups[0][0], "last_kernel_done_ms": groups[-1][1]}
 
     # ---- secondary legs (every rank takes part; each is exact-checked) ---------------------------
     _lib.check(zk.zk_table_free(handle.value))
@@ -475,11 +487,12 @@ def run_gpu_arm(args):
 
     if rank == 0:
         c, W = int(info[0]), int(info[1])
-        # kernels of libzkb200 launched in the timed region: 5 per MSM (digit count pass with the scalar
-        # check, 2 scan kernels, digit scatter pass, accumulate) + one batched tail per group (2 partial
-        # fix-ups, reduce chunks, tree levels, combine+finalize) + the shard sum for N > 1
+        # kernels of libzkb200 launched in the timed region, per group of queued MSMs: 5 for the sort and
+        # the accumulation (digit count pass with the scalar check, 2 scan kernels, digit scatter pass,
+        # k_accumulate) + the batched tail (2 partial fix-ups, reduce chunks, tree levels,
+        # combine+finalize) + the shard sum for N > 1
         group = QUEUE if pipelined else 1
-        groups = (args.steps + group - 1) // group
+        groups = max(timed_joins, (args.steps + group - 1) // group)     # a table beyond 2^21 points joins more often
         cpw = (1 << (c - 1)) // (16 if (pipelined and min(group, args.steps) >= 3) else 4)
         levels, cnt = 0, cpw
         while True:
@@ -487,8 +500,10 @@ def run_gpu_arm(args):
             cnt = (cnt + 63) // 64
             if cnt == 1:
                 break
-        gpu_launches = 5 * args.steps + groups * (4 + levels + (1 if world > 1 else 0))
-        acc_avg = sum(acc_ms) / len(acc_ms)
+        gpu_launches = groups * (5 + 4 + levels + (1 if world > 1 else 0))
+        assert timed_msms == args.steps or timed_joins == 64, (timed_joins, groups, timed_msms)   # the ring keeps 64 joins
+        acc_avg = timed_stage_ms[1] / timed_msms                 # k_accumulate time per MSM inside the timed region
+        acc_single = sum(acc_ms) / len(acc_ms)                   # ... of a single-MSM launch after it
         achieved = n * MAC32_PER_POINT / (acc_avg * 1e-3) / 1e12
         peaks = {}
         try:
@@ -521,7 +536,11 @@ def run_gpu_arm(args):
             "roofline": {"bound": "int32-imad", "kernel": "k_accumulate<Fp>", "achieved": achieved,
                          "peak": peak_mac32 / 1e12, "unit": "TMAC32/s", "frac": achieved / (peak_mac32 / 1e12),
                          "traffic": (NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.logn == 20 and c == 17) else None),
-                         "traffic_source": "profiles/r01_ncu_accumulate.md (ncu --set full, dram__bytes_read+write per launch)", "kernel_ms": acc_avg, "stages_ms_last_step": stages_last,
+                         "traffic_source": "profiles/r01_ncu_accumulate.md (ncu --set full, dram__bytes_read+write per 2^20-point MSM)",
+                         "kernel_ms": acc_avg, "kernel_ms_note": "k_accumulate launch durations summed over the timed region (CUDA events on the launching stream) / MSMs processed; one launch accumulates all the MSMs of a join",
+                         "launches_in_timed_region": timed_joins, "msms_per_launch": timed_msms / max(timed_joins, 1),
+                         "timed_region_stage_ms_per_step": [x / timed_msms for x in timed_stage_ms],
+                         "kernel_ms_single_msm_launch": acc_single, "stages_ms_last_step": stages_last,
                          "algorithmic_mac32_per_point": MAC32_PER_POINT,
                          "peak_source": "mad.lo.cc/madc.hi.cc chains measured in this process (zk_bench_intpipe), /2",
                          "whole_step_frac": n_total / world * MAC32_PER_POINT / (dev_ms / args.steps * 1e-3) / peak_mac32,

@@ -84,9 +84,11 @@ int zk_g2_table_load(const uint8_t *bases, const uint8_t *inf_flags, size_t n, i
 int zk_g1_table_msm(uint64_t handle, const uint8_t *scalars, size_t n, uint8_t out[ZK_G1_OUT]);
 int zk_g2_table_msm(uint64_t handle, const uint8_t *scalars, size_t n, uint8_t out[ZK_G2_OUT]);
 /* `count` MSMs over the first n table points: scalars[i] points to the i-th host scalar vector,
- * out receives count point results.  The uploads are double-buffered against the computation and
- * the tails are batched, so a caller with many MSMs over one key (a stream of proofs) gets the
- * device-resident rate end to end.  Pinned host memory makes the uploads asynchronous. */
+ * out receives count point results.  The MSMs run in groups (a short first group, then up to the
+ * queue depth): a group is uploaded on a copy stream while the previous group is accumulated, and
+ * sorted, accumulated and reduced as one launch sequence, so a caller with many MSMs over one key
+ * (a stream of proofs) gets the device-resident rate end to end.  Pinned host memory makes the
+ * uploads asynchronous. */
 int zk_g1_table_msm_batch(uint64_t handle, const uint8_t *const *scalars, size_t n, size_t count, uint8_t *out);
 int zk_g2_table_msm_batch(uint64_t handle, const uint8_t *const *scalars, size_t n, size_t count, uint8_t *out);
 /* Same with device-resident scalars / result, enqueued on `cuda_stream` (a cudaStream_t,
@@ -99,24 +101,34 @@ int zk_g2_table_msm_dev(uint64_t handle, const void *d_scalars, size_t n, void *
  * [4] = 1 (legacy field), [5] = device bytes (all devices), [6] = points, [7] = precomputed;
  * c / W are those of the primary device's part when the table is spread over several devices */
 int zk_table_info(uint64_t handle, uint64_t info[8]);
-/* Pipelining of consecutive *_msm_dev calls on one table.  Each MSM ends in a latency-bound
- * tail (bucket reduction, window combine, affine conversion: ~40 dependent point operations) whose
- * wall time is the same for one MSM as for a batch.  With enable = 0 (default) every call runs its
- * own tail: plain stream order.  With enable != 0 a call only sorts and accumulates into one of 16
- * bucket buffers and queues its tail; zk_table_join(handle, cuda_stream) (or the 17th call) runs
- * ONE batched tail for everything queued.  d_out of a queued call is valid on cuda_stream after
- * the join. */
+/* Pipelining of consecutive *_msm_dev calls on one table.  With enable = 0 (default) every call
+ * runs its MSM at once: plain stream order.  With enable != 0 a call only QUEUES its MSM (scalar
+ * pointer, count, output slot) and zk_table_join(handle, cuda_stream) — or a call that finds the
+ * queue full — runs everything queued as ONE launch sequence: one counting sort and one balanced
+ * accumulation over all the queued MSMs' buckets, then one batched tail (bucket reduction, affine
+ * conversion: ~40 dependent point operations whose wall time is the same for one MSM as for a
+ * batch).  enable = 1: default depth (32 MSMs per join, or ZKB200_QUEUE; fewer for tables beyond
+ * 2^21 points, whose sorted entry lists are kept below 2 GB); enable = 2..32: that depth.
+ * d_scalars of a queued call must stay valid and unchanged, and d_out is valid on cuda_stream,
+ * after the join. */
 int zk_table_pipeline(uint64_t handle, int enable);
 int zk_table_join(uint64_t handle, void *cuda_stream);
-/* Stage timing for the roofline leg of bench.py: enable != 0 makes the following MSMs on this
- * table bracket their stages with CUDA events on the launching stream; stage_ms (nullable)
- * receives the last profiled run's times once that stream has been synchronised:
+/* Stage timing for the roofline leg of bench.py: enable != 0 makes the following joins on this
+ * table (one per MSM unless pipelined) bracket their stages with CUDA events on the launching
+ * stream; stage_ms (nullable) receives the last profiled join's times once that stream has been
+ * synchronised:
  * [0] digits + scan + scatter, [1] bucket accumulation, [2] bucket reduction, [3] window combine. */
 int zk_table_profile(uint64_t handle, int enable, float stage_ms[4]);
+/* Sums of those stage times over every join recorded since profiling was switched on (at most the
+ * last 64 joins): counts[0] = MSMs the joins held, counts[1] = joins.  With a pipelined table one join
+ * sorts and accumulates all its queued MSMs in one launch sequence, so the accumulation kernel's
+ * time per MSM inside a timed region is totals[1] / counts[0]. */
+int zk_table_profile_totals(uint64_t handle, float totals[4], uint64_t counts[2]);
 /* Per-step timing of zk_g*_table_msm_batch (bench.py's e2e leg): enable != 0 makes the following
  * batch calls on this table record, for each of their first 64 steps, when its upload started and
- * ended (copy stream) and when its first and last kernel ran (compute stream).  out (nullable, with
- * steps) receives 4 floats per step of the LAST batch call, in ms since its first upload started. */
+ * ended (copy stream) and when the kernels of its GROUP (the steps joined together) started and
+ * ended (compute stream).  out (nullable, with steps) receives 4 floats per step of the LAST batch
+ * call, in ms since its first upload started. */
 int zk_table_batch_timing(uint64_t handle, int enable, float *out, size_t cap, size_t *steps);
 int zk_table_free(uint64_t handle);
 
@@ -230,6 +242,10 @@ typedef struct {
 /* Device time (ms, CUDA events on the primary device's stream: first upload to last download) of
  * the last zk_groth16_prove* call on this key; for bench.py. */
 int zk_groth16_last_device_ms(uint64_t pk, float *ms);
+/* Stage split of that time, in ms: [0] witness upload, [1] QAP evaluation + quotient h(x),
+ * [2] MSM scalars, [3] A, [4] C and [5] B sorted and accumulated (the primary device's part),
+ * [6] batched tails of the three MSMs, [7] wait for the other devices + combine + download. */
+int zk_groth16_last_stage_ms(uint64_t pk, float out[8]);
 
 int zk_pinocchio_pk_load(const zk_pinocchio_pkey *pk, int shard_index, int shard_count, uint64_t *handle);
 /* d = dv | dw | dy (3 * 32 B, the draws of pinocchio.ml:428-430) selects ZK.prove (:559-561);

@@ -121,7 +121,7 @@ def test_table_msm_batch_and_pipelined_dev(zk):
     import numpy as np
     import torch
     from zukelang_b200 import _lib
-    n, count = 3000, 19
+    n, count = 3000, 35            # the batch call queues up to 32 tails: 35 overflows the queue once
     rng = random.Random(77)
     dl = [rng.randrange(R) for _ in range(n)]
     bases = (ctypes.c_uint8 * (96 * n))()
@@ -138,8 +138,8 @@ def test_table_msm_batch_and_pipelined_dev(zk):
         out = (ctypes.c_uint8 * (144 * count))()
         _lib.check(zk.zk_g1_table_msm_batch(h.value, ptrs, n, count, out))
         assert [bytes(out[i * 144:(i + 1) * 144]) for i in range(count)] == expect
-        # pipelined device calls + join
-        _lib.check(zk.zk_table_pipeline(h.value, 1))
+        # pipelined device calls + join, queue depth 4: the 5th, 9th, ... call finds the queue full
+        _lib.check(zk.zk_table_pipeline(h.value, 4))
         d_sc = [torch.from_numpy(np.frombuffer(v.raw, dtype=np.uint8).copy()).cuda() for v in vecs]
         d_out = torch.zeros(count, 144, dtype=torch.uint8, device="cuda")
         st = torch.cuda.Stream()

@@ -3,7 +3,7 @@
    Runs the UNMODIFIED functors  Groth16.Make / Pinocchio.Make  (src/groth16/groth16.ml,
    src/pinocchio/pinocchio.ml) over Curve.Bls12_381 arithmetic (opam bls12-381 6.1.0) on small
    hand-built circuits and prints ONE JSON document with everything a byte-for-byte comparison needs:
-   the gates in the order QAP.build assigned them to the domain points 1..n (QAP.ml:18-94), every
+   the gates in the order QAP.build assigned them to the domain points 0..n-1 (QAP.ml:18-94), every
    scalar the protocol drew, the witness, and pkey / vkey / proof through the reference's own
    [@@deriving yojson] converters.
 

@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkb200.so")
+# ZKB200_LIB selects another build of the same library (libzkb200_checked.so: device-side asserts on)
+LIB_PATH = os.environ.get("ZKB200_LIB") or os.path.join(_HERE, "libzkb200.so")
 
 ZK_OK, ZK_EARG, ZK_EPOINT, ZK_ECUDA, ZK_EREMAINDER = 0, -1, -2, -3, -4
 FR_BYTES, G1_RAW, G1_COMP, G1_OUT, G2_RAW, G2_COMP, G2_OUT = 32, 96, 48, 144, 192, 96, 288
@@ -51,6 +52,7 @@ SIGNATURES = {
     "zk_g2_table_msm_dev": (c_int, [c_uint64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zk_table_info": (c_int, [c_uint64, POINTER(c_uint64)]),
     "zk_table_pipeline": (c_int, [c_uint64, c_int]),
+    "zk_table_profile_totals": (c_int, [c_uint64, POINTER(ctypes.c_float), POINTER(ctypes.c_uint64)]),
     "zk_table_join": (c_int, [c_uint64, c_void_p]),
     "zk_table_profile": (c_int, [c_uint64, c_int, c_void_p]),
     "zk_table_batch_timing": (c_int, [c_uint64, c_int, c_void_p, c_size_t, POINTER(c_size_t)]),
@@ -72,6 +74,7 @@ SIGNATURES = {
     "zk_groth16_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zk_groth16_prove_coeffs": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zk_groth16_last_device_ms": (c_int, [c_uint64, POINTER(ctypes.c_float)]),
+    "zk_groth16_last_stage_ms": (c_int, [c_uint64, POINTER(ctypes.c_float)]),
     "zk_eval_domain_load": (c_int, [c_size_t, c_void_p, c_void_p, POINTER(c_uint64)]),
     "zk_r1cs_load": (c_int, [c_uint64, c_int, c_size_t, c_void_p, c_void_p, c_void_p]),
     "zk_groth16_prove_r1cs": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -2,6 +2,16 @@
 // reporting, stream-ordered device buffers, vector load/store and the byte
 // formats of the C ABI (include/zkb200.h).
 #pragma once
+// Bounds checks of our own (compute-sanitizer is not available on the B200 pool): a build with
+// -DZK_CHECKED (`make CHECKED=1` -> libzkb200_checked.so, selected with ZKB200_LIB) turns every
+// ZK_DCHECK into a device-side assert — an out-of-range index then stops the kernel with file and
+// line on stderr and the next API call fails — and costs nothing in the product build.
+#ifdef ZK_CHECKED
+#include <assert.h>
+#define ZK_DCHECK(cond) assert(cond)
+#else
+#define ZK_DCHECK(cond) ((void)0)
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

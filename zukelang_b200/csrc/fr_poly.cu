@@ -146,7 +146,11 @@ k_ntt_pass(Fr* __restrict__ x, const Fr* __restrict__ tw, uint32_t D, int logD, 
   const uint32_t tiles_per_hi = 1u << (L - logC);
   const uint32_t hi = blockIdx.x / tiles_per_hi, lowbase = (blockIdx.x % tiles_per_hi) << logC;
   const size_t base = ((size_t)hi << (logD - P.s0)) + lowbase;
-  auto gidx = [&](uint32_t e) { return base + ((size_t)(e >> logC) << L) + (e & (C - 1)); };
+  auto gidx = [&](uint32_t e) {
+    const size_t g = base + ((size_t)(e >> logC) << L) + (e & (C - 1));
+    ZK_DCHECK(g < D);
+    return g;
+  };
   for (uint32_t e = threadIdx.x; e < tile; e += NTT_THREADS) {
     const uint4* src = reinterpret_cast<const uint4*>(&v[gidx(e)]);
     ntt_tile[e] = src[0];
@@ -168,6 +172,7 @@ k_ntt_pass(Fr* __restrict__ x, const Fr* __restrict__ tw, uint32_t D, int logD, 
       uint4* b4 = reinterpret_cast<uint4*>(&b);
       a4[0] = ntt_tile[e0]; a4[1] = ntt_tile[tile + e0];
       b4[0] = ntt_tile[e1]; b4[1] = ntt_tile[tile + e1];
+      ZK_DCHECK(((size_t)j << s) < D / 2 && e1 < tile);
       const Fr w = load_vec(&tw[(size_t)j << s]);
       Fr r0, r1;
       if (INVERSE) { b = b * w; r0 = a + b; r1 = a - b; }
@@ -411,13 +416,16 @@ struct CsrPtrs {
   const Fr* val[3];
 };
 static __global__ void __launch_bounds__(128)
-k_csr_matvec(CsrPtrs m, const Fr* __restrict__ sol, uint32_t n, Fr* __restrict__ out) {
+k_csr_matvec(CsrPtrs m, const Fr* __restrict__ sol, uint32_t n, uint32_t n_vars, Fr* __restrict__ out) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   int which = blockIdx.y;
   const uint32_t* rp = m.row_ptr[which];
   Fr acc = Fr::zero();
-  for (uint32_t k = rp[j]; k < rp[j + 1]; k++) acc = acc + load_vec(&m.val[which][k]) * load_vec(&sol[m.col[which][k]]);
+  for (uint32_t k = rp[j]; k < rp[j + 1]; k++) {
+    ZK_DCHECK(m.col[which][k] < n_vars);
+    acc = acc + load_vec(&m.val[which][k]) * load_vec(&sol[m.col[which][k]]);
+  }
   store_vec(&out[(size_t)which * n + j], acc);
 }
 // gate check V(j) W(j) == Y(j) and a = w .* evals zero-padded to D (3 vectors)
@@ -538,7 +546,7 @@ void EvalDomain::eval(const uint32_t* d_sol_raw, cudaStream_t st) {
   fr_to_mont(d_sol_raw, sol_m.p, m, flag.p, st);
   CsrPtrs P;
   for (int q = 0; q < 3; q++) { P.row_ptr[q] = mat[q].row_ptr.p; P.col[q] = mat[q].col.p; P.val[q] = mat[q].val.p; }
-  k_csr_matvec<<<dim3(cdiv(n, 128), 3), 128, 0, st>>>(P, sol_m.p, n, evals.p);
+  k_csr_matvec<<<dim3(cdiv(n, 128), 3), 128, 0, st>>>(P, sol_m.p, n, m, evals.p);
   k_eval_prepare<<<cdiv(D, 128), 128, 0, st>>>(evals.p, w.p, n, D, work.p, flag.p + 1);
   ntt_forward_batch(plan, work.p, 3, st);
   k_mul_by_ghat<<<cdiv(D, 256), 256, 0, st>>>(work.p, ghat.p, D);

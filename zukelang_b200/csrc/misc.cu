@@ -256,10 +256,23 @@ int zk_table_profile(uint64_t handle, int enable, float stage_ms[4]) {
   auto go = [&](auto* h) {          // stage times of the primary device's part
     auto& t = h->parts[0]->table;
     if (stage_ms) t.stage_ms(stage_ms);
-    for (auto& p : h->parts) p->table.profile = enable != 0;
+    for (auto& p : h->parts) p->table.set_profile(enable != 0);
   };
   if (hb->kind == 1) go(static_cast<TableHandle<G1Traits>*>(hb));
   else go(static_cast<TableHandle<G2Traits>*>(hb));
+  ZK_API_END
+}
+
+// Sums of the stage times over the joins recorded since profiling was switched on (at most the last
+// 64), primary device's part: totals[0..3] as in zk_table_profile, counts[0] = MSMs in those joins,
+// counts[1] = joins.  The launching stream must have been synchronised.
+int zk_table_profile_totals(uint64_t handle, float totals[4], uint64_t counts[2]) {
+  ZK_API_BEGIN
+  using namespace zk;
+  HandleBase* hb = lookup_handle(handle, 0);
+  ZK_REQUIRE((hb->kind == 1 || hb->kind == 2) && totals && counts, ZK_EARG, "table_profile_totals: bad arguments");
+  if (hb->kind == 1) static_cast<TableHandle<G1Traits>*>(hb)->parts[0]->table.stage_totals(totals, &counts[0], &counts[1]);
+  else static_cast<TableHandle<G2Traits>*>(hb)->parts[0]->table.stage_totals(totals, &counts[0], &counts[1]);
   ZK_API_END
 }
 
@@ -282,7 +295,7 @@ int zk_table_pipeline(uint64_t handle, int enable) {
   auto go = [&](auto* h) {
     auto& t = h->single();
     if (!enable && t.queued) { ZK_CUDA(cudaDeviceSynchronize()); t.join(default_stream()); ZK_CUDA(cudaStreamSynchronize(default_stream())); }
-    t.set_pipelined(enable != 0);
+    t.set_pipelined(enable != 0, enable > 1 ? enable : 0);   // enable > 1 = queue depth
   };
   if (hb->kind == 1) go(static_cast<TableHandle<G1Traits>*>(hb));
   else go(static_cast<TableHandle<G2Traits>*>(hb));

@@ -6,7 +6,10 @@
 // (sum_apply_powers) — by one bucket-method MSM per proof element.  The result
 // is the same group element, hence the same serialised bytes.
 //
-// Pipeline (all on the caller's stream, no host round trips):
+// Pipeline (all on the caller's stream, no host round trips).  A pipelined table QUEUES its MSMs
+// (scalar pointer, range, output slots) and join() runs everything queued — up to 32 MSMs over the
+// same bases — as ONE launch sequence: queued MSM q owns the buckets [q * nb, (q + 1) * nb), so the
+// Q MSMs are one counting sort and one balanced accumulation over Q * nb buckets:
 //   1. k_digits<COUNT>    scalar -> (negate if > (r-1)/2) -> signed c-bit digits -> bucket histogram
 //   2. k_scan_*           exclusive prefix sum of the histogram
 //   3. k_digits<SCATTER>  (bucket, point) pairs placed by counting sort
@@ -14,15 +17,19 @@
 //                         with XYZZ mixed adds (paired interleaved products, dedicated squares)
 //      k_fix_partials / k_fix_heavy   buckets split over several slices: add up their pieces
 //   5. k_reduce_chunks    running-sum reduction of L buckets per thread        } the latency-bound
-//      k_reduce_tree      per-window tree sum of the chunk results             } tail: deferred and
-//   6. k_combine_finalize window combine (a copy when precomputed), affine     } batched over up to
-//                         conversion, wire bytes                               } 16 queued MSMs
+//      k_reduce_tree      per-window tree sum of the chunk results             } tail: one batched
+//   6. k_combine_finalize window combine (a copy when precomputed), affine     } launch for all the
+//                         conversion, wire bytes                               } queued MSMs
+// Batching the sort and the accumulation (not only the tail) matters for small shards (2^17 points
+// per GPU on 8 GPUs): the at most 2 T partial bucket pieces of the T accumulation threads, the
+// five launches and their gaps are paid once per join instead of once per MSM.
 //
 // A BaseTable built with `precompute` holds 2^(c*w) * P_i for every window w, so all windows
 // share ONE set of 2^(c-1) buckets: the bucket reduction shrinks W times and the window combine
 // disappears, at the price of W times the table bytes — cheap against 180 GB of HBM3e.
 #pragma once
 #include <exception>
+#include <vector>
 #include "common.cuh"
 
 namespace zk {
@@ -53,20 +60,34 @@ __device__ __forceinline__ uint32_t scalar_bits(const uint32_t* k, int pos, int 
   return (uint32_t)(((hi << 32) | lo) >> sh) & ((1u << c) - 1);
 }
 
+// The MSMs of one join (kernel parameter, by value): MSM q reads count[q] canonical scalars at
+// scalars[q] and applies them to the table points [first[q], first[q] + count[q]) (a table may hold
+// several key queries back to back); err[q] (nullable) is set when a scalar is >= r.
+constexpr int MSM_QUEUE = 32;   // most MSMs one join can take (slot tables are kernel parameters)
+struct QueueSlots {
+  const uint32_t* scalars[MSM_QUEUE];
+  int* err[MSM_QUEUE];
+  uint32_t count[MSM_QUEUE];
+  uint32_t first[MSM_QUEUE];
+};
+
 // Steps 1 and 3.  Signed-digit recoding.  A scalar k > (r-1)/2 is first replaced by r - k with
 // every digit sign flipped (k P = (r - k)(-P)), which bounds the recoded value by 2^254 and saves
 // a window for c = 17, 19, 20.  Digits d lie in [-(2^(c-1) - 1), 2^(c-1)] with a carry into the
 // next window; zero digits (and identity bases) emit nothing.
 // entry = point index (w * stride + i when precomputed, else i) | sign << 31;
-// n = scalars in this call, first = index of the first table point they apply to (a table may
-// hold several key queries back to back), stride = points per window of the table.
+// blockIdx.y = queued MSM (its buckets start at blockIdx.y * nbuckets), stride = points per window
+// of the table.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256)
-k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip, uint32_t n, uint32_t first,
-         uint32_t stride, MsmConfig cfg, uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries,
-         int* __restrict__ err) {
+k_digits(QueueSlots q, const uint8_t* __restrict__ skip, uint32_t stride, MsmConfig cfg,
+         uint32_t* __restrict__ counts_or_cursor, uint32_t* __restrict__ entries, uint32_t entries_cap) {
+  const int z = blockIdx.y;
+  const uint32_t n = q.count[z], first = q.first[z];
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const uint32_t* __restrict__ scalars = q.scalars[z];
+  int* err = q.err[z];
   uint32_t k[8];
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * (size_t)i);
   uint4 a = __ldg(sp), b = __ldg(sp + 1);
@@ -76,6 +97,12 @@ k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip,
 #pragma unroll
     for (int j = 0; j < 8; j++) m[j] = FrParams::mod(j);
     if (Fr::geq_raw(k, m)) { atomicExch(err, 1); return; }
+  }
+  if (SCATTER && err) {    // the count pass skipped this scalar: skip it here too
+    uint32_t m[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) m[j] = FrParams::mod(j);
+    if (Fr::geq_raw(k, m)) return;
   }
   if (skip && skip[first + i]) return;
   if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) return;
@@ -93,15 +120,18 @@ k_digits(const uint32_t* __restrict__ scalars, const uint8_t* __restrict__ skip,
   }
   uint32_t carry = 0;
   const uint32_t half = cfg.B;  // 2^(c-1)
+  const uint32_t zbase = (uint32_t)z * cfg.nbuckets();
   for (int w = 0; w < cfg.W; w++) {
     uint32_t d = scalar_bits(k, w * cfg.c, cfg.c) + carry;
     uint32_t neg = flip;
     if (d > half) { d = (1u << cfg.c) - d; neg ^= 1; carry = 1; } else carry = 0;
     if (d == 0) continue;
-    uint32_t bucket = (cfg.nwb == 1 ? 0u : (uint32_t)w * cfg.B) + d - 1;
+    uint32_t bucket = zbase + (cfg.nwb == 1 ? 0u : (uint32_t)w * cfg.B) + d - 1;
+    ZK_DCHECK(d - 1 < cfg.B && bucket < gridDim.y * cfg.nbuckets());
     if (SCATTER) {
       uint32_t pos = atomicAdd(&counts_or_cursor[bucket], 1u);
       uint32_t idx = (cfg.nwb == 1) ? (uint32_t)w * stride + first + i : first + i;
+      ZK_DCHECK(pos < entries_cap && first + i < stride);
       entries[pos] = idx | (neg << 31);
     } else {
       atomicAdd(&counts_or_cursor[bucket], 1u);
@@ -210,7 +240,7 @@ template <class F, int MINB, bool STAGED, bool PAIRED = false>
 __global__ void __launch_bounds__(ACC_THREADS, MINB)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums, XYZZ<F>* __restrict__ partial,
-             uint32_t nbuckets) {
+             uint32_t nbuckets, uint32_t npoints) {
   extern __shared__ uint4 acc_stage[];   // [2][VEC][ACC_THREADS] when STAGED: conflict-free 16-byte columns
   constexpr int VEC = sizeof(Affine<F>) / 16;
   const uint32_t T = gridDim.x * blockDim.x;
@@ -222,6 +252,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
   const uint32_t e0 = (uint32_t)e0_64;
   const uint32_t e1 = min(E, e0 + per);
   auto issue = [&](int buf, uint32_t ent) {
+    ZK_DCHECK((ent & 0x7fffffffu) < npoints);
     const uint4* src = reinterpret_cast<const uint4*>(&bases[ent & 0x7fffffffu]);
 #pragma unroll
     for (int j = 0; j < VEC; j++) cp_async16(&acc_stage[(buf * VEC + j) * ACC_THREADS + threadIdx.x], src + j);
@@ -241,7 +272,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
   }
   uint32_t b = lo;
   uint32_t b_end = offsets[b + 1];
-  while (b_end <= e0) { b++; b_end = offsets[b + 1]; }   // skip empty buckets sharing the offset
+  while (b_end <= e0) { b++; ZK_DCHECK(b < nbuckets); b_end = offsets[b + 1]; }   // skip empty buckets sharing the offset
   uint32_t seg_start = e0;
   XYZZ<F> acc = XYZZ<F>::inf();
   Affine<F> cur;
@@ -258,7 +289,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
         const bool complete = seg_start == offsets[b];
         store_vec(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);   // incomplete => started before e0
         acc = XYZZ<F>::inf();
-        do { b++; b_end = offsets[b + 1]; } while (b_end <= k);
+        do { b++; ZK_DCHECK(b < nbuckets); b_end = offsets[b + 1]; } while (b_end <= k);
         seg_start = k;
       }
       if (more) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -274,54 +305,48 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
         const bool complete = seg_start == offsets[b];
         store_vec(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);
         acc = XYZZ<F>::inf();
-        do { b++; b_end = offsets[b + 1]; } while (b_end <= k);
+        do { b++; ZK_DCHECK(b < nbuckets); b_end = offsets[b + 1]; } while (b_end <= k);
         seg_start = k;
       }
       e = entries[k];
+      ZK_DCHECK((e & 0x7fffffffu) < npoints);
       cur = load_vec(&bases[e & 0x7fffffffu]);
       if (e >> 31) cur.y = cur.y.neg();
       if constexpr (PAIRED) acc.madd_paired(cur); else acc.madd(cur);
     }
   }
   // last piece: bucket b from seg_start to e1
+  ZK_DCHECK(b < nbuckets && 2 * (size_t)t + 1 < 2 * (size_t)T);
   const bool starts_here = seg_start == offsets[b];
   const bool ends_here = e1 == b_end;
   if (starts_here && ends_here) store_vec(&bucket_sums[b], acc);
   else store_vec(&partial[2 * (size_t)t + (e0 >= offsets[b] ? 0 : 1)], acc);
 }
 
-// Per-slot geometry of the deferred fix-up (passed by value): T = threads the accumulation of the
-// queued MSM in that slot ran with.
-constexpr int MSM_QUEUE = 16;
-struct TailSlots {
-  uint32_t T[MSM_QUEUE];
-};
-
-// Step 4b (deferred, batched: blockIdx.z = queued MSM): one thread per bucket: empty buckets become
-// the identity; a bucket split over a few slices gets the sum of its pieces (slot rule as in
-// k_accumulate).  Buckets split over more than HEAVY_PIECES slices (skewed scalars)
-// are queued for k_fix_heavy.
+// Step 4b: one thread per bucket (all queued MSMs: nbuckets = Q * nb): empty buckets become the
+// identity; a bucket split over a few slices gets the sum of its pieces (slot rule as in
+// k_accumulate; T = threads the accumulation ran with).  Buckets split over more than HEAVY_PIECES
+// slices (skewed scalars) are queued for k_fix_heavy.
 constexpr uint32_t HEAVY_PIECES = 8;
 template <class F>
 __global__ void __launch_bounds__(128)
-k_fix_partials(const uint32_t* __restrict__ offsets_all, XYZZ<F>* __restrict__ bucket_sums_all,
-               const XYZZ<F>* __restrict__ partial_all, uint32_t nbuckets, size_t partial_stride, TailSlots slots,
-               uint32_t* __restrict__ heavy_all, size_t heavy_stride) {
+k_fix_partials(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums,
+               const XYZZ<F>* __restrict__ partial, uint32_t nbuckets, uint32_t T, uint32_t* __restrict__ heavy) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
-  const int z = blockIdx.z;
-  const uint32_t* offsets = offsets_all + (size_t)z * (nbuckets + 1);
-  XYZZ<F>* bucket_sums = bucket_sums_all + (size_t)z * nbuckets;
-  const XYZZ<F>* partial = partial_all + (size_t)z * partial_stride;
-  uint32_t* heavy = heavy_all + (size_t)z * heavy_stride;
-  const uint32_t T = slots.T[z];
   const uint32_t E = offsets[nbuckets];
   const uint32_t lo = offsets[b], hi = offsets[b + 1];
   if (lo == hi) { store_vec(&bucket_sums[b], XYZZ<F>::inf()); return; }
   const uint32_t per = (E + T - 1) / T;
   const uint32_t t_first = lo / per, t_last = (hi - 1) / per;
+  ZK_DCHECK(lo <= hi && hi <= E && t_last < T);
   if (t_first == t_last) return;  // written whole by its slice
-  if (t_last - t_first + 1 > HEAVY_PIECES) { heavy[1 + atomicAdd(heavy, 1u)] = b; return; }
+  if (t_last - t_first + 1 > HEAVY_PIECES) {
+    const uint32_t slot = atomicAdd(heavy, 1u);
+    ZK_DCHECK(slot + 1 < T / 4 + 2);   // heavy queue capacity: a heavy bucket spans > 8 of the T slices
+    heavy[1 + slot] = b;
+    return;
+  }
   XYZZ<F> acc = XYZZ<F>::inf();
   for (uint32_t t = t_first; t <= t_last; t++) {
     const uint32_t slot = ((uint64_t)t * per >= lo) ? 0 : 1;
@@ -331,25 +356,17 @@ k_fix_partials(const uint32_t* __restrict__ offsets_all, XYZZ<F>* __restrict__ b
   store_vec(&bucket_sums[b], acc);
 }
 
-// Step 4c: heavy buckets, one BLOCK each (grid-stride over the queue; blockIdx.z = queued MSM):
-// threads stride over the pieces, a shared-memory tree adds the per-thread sums: pieces / blockDim +
-// log2(blockDim) sequential additions (a 2^20-point MSM whose scalars are half ones has a
-// 17 000-piece bucket).
+// Step 4c: heavy buckets, one BLOCK each (grid-stride over the queue): threads stride over the
+// pieces, a shared-memory tree adds the per-thread sums: pieces / blockDim + log2(blockDim)
+// sequential additions (a 2^20-point MSM whose scalars are half ones has a 17 000-piece bucket).
 template <class F>
 __global__ void __launch_bounds__(256)
-k_fix_heavy(const uint32_t* __restrict__ offsets_all, XYZZ<F>* __restrict__ bucket_sums_all,
-            const XYZZ<F>* __restrict__ partial_all, uint32_t nbuckets, size_t partial_stride, TailSlots slots,
-            const uint32_t* __restrict__ heavy_all, size_t heavy_stride) {
+k_fix_heavy(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums,
+            const XYZZ<F>* __restrict__ partial, uint32_t nbuckets, uint32_t T, const uint32_t* __restrict__ heavy) {
   extern __shared__ uint4 smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
-  const int z = blockIdx.z;
-  const uint32_t* heavy = heavy_all + (size_t)z * heavy_stride;
   const uint32_t count = heavy[0];
   if (count == 0) return;   // block-uniform
-  const uint32_t* offsets = offsets_all + (size_t)z * (nbuckets + 1);
-  XYZZ<F>* bucket_sums = bucket_sums_all + (size_t)z * nbuckets;
-  const XYZZ<F>* partial = partial_all + (size_t)z * partial_stride;
-  const uint32_t T = slots.T[z];
   const uint32_t E = offsets[nbuckets];
   const uint32_t per = (E + T - 1) / T;
   for (uint32_t q = blockIdx.x; q < count; q += gridDim.x) {   // block-uniform
@@ -575,25 +592,27 @@ struct BaseTable {
   MsmConfig cfg{};
   DevBuf<Affine<F>> pts;     // n points, or W * n when precomputed (window-major)
   DevBuf<uint8_t> skip;      // 1 = identity base
-  // workspace (reused by every MSM on this table; calls on one table are stream-ordered)
-  DevBuf<uint32_t> counts, cursor, tile_sums, entries;   // counts is all zero between MSMs (k_scan_apply clears it)
-  DevBuf<uint32_t> offsets, heavy;   // one slot per queued MSM: bucket offsets (nb + 1); heavy[0] = queue length, then the queue
-  // Deferred tails.  The latency-bound end of an MSM (bucket reduction, window combine, affine
-  // conversion: ~40 dependent point operations) costs the same wall time for one MSM as for a batch,
-  // so a pipelined table queues up to MSM_QUEUE accumulated MSMs (one bucket_sums slot each) and
-  // finishes them with ONE batched launch sequence on the caller's stream (flush / join).
-  DevBuf<XYZZ<F>> bucket_sums, partial, chunk_out, tree_tmp, window_sums;   // queue_cap slots each
-  TailSlots slot_geom{};     // accumulation threads of every queued MSM (for the deferred fix-up)
-  size_t partial_stride = 0, heavy_stride = 0;
+  // workspace (reused by every join on this table; calls on one table are stream-ordered).  Sized
+  // for queue_cap queued MSMs: queued MSM q owns buckets [q * nb, (q + 1) * nb).
+  DevBuf<uint32_t> counts, cursor, tile_sums, entries;   // counts is all zero between joins (k_scan_apply clears it)
+  DevBuf<uint32_t> offsets, heavy;   // bucket offsets (queue_cap * nb + 1); heavy[0] = queue length, then the queue
+  // Queued MSMs.  run() only records the MSM (scalar pointer, range, output slots); join() sorts,
+  // accumulates and reduces everything queued with ONE launch sequence on the caller's stream: the
+  // latency-bound end of an MSM (bucket reduction, window combine, affine conversion: ~40 dependent
+  // point operations) costs the same wall time for one MSM as for a batch, and so do the partial
+  // pieces and the launch gaps of the sort and the accumulation.  A table that is not pipelined
+  // joins inside every run().  The scalars of a queued MSM must stay valid until its join has run.
+  DevBuf<XYZZ<F>> bucket_sums, partial, chunk_out, tree_tmp, window_sums;
   uint32_t acc_blocks = 0;   // persistent grid of k_accumulate: resident blocks per SM x SMs
   int acc_variant = 0;       // ZKB200_ACC_VARIANT[_G2]: see build_tables (9 / 5 = cp.async-staged defaults for G1 / G2)
   template <class Fn> void acc_dispatch(Fn&& fn);
   int acc_occupancy();
-  void acc_launch(uint32_t grid, const uint32_t* off, XYZZ<F>* bsum, XYZZ<F>* part, cudaStream_t st);
+  void acc_launch(uint32_t grid, uint32_t nbuckets, cudaStream_t st);
   int queued = 0;
-  int queue_cap = 0;         // bucket buffers currently allocated (1 unless pipelined)
+  int queue_cap = 0;         // MSMs one join can take with the buffers currently allocated (1 unless pipelined)
+  QueueSlots slots{};
   TailOutputs<F> outs{};
-  bool pipelined = false;    // false: every run() flushes immediately (plain stream order)
+  bool pipelined = false;    // false: every run() joins immediately (plain stream order)
 
   static MsmConfig choose_config(uint32_t n, bool precompute, int force_c);
   void load(const uint8_t* host_raw, const uint8_t* host_inf, uint32_t n, bool precompute, int force_c,
@@ -604,10 +623,13 @@ struct BaseTable {
   // d_err (nullable): set to 1 when a scalar is not canonical (>= r).
   void run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes, cudaStream_t st,
            uint32_t first = 0, int* d_err = nullptr);
-  // finish every queued MSM on `st` (batched tail); results are valid in stream order afterwards
-  void join(cudaStream_t st);
-  // pipelined = queue up to MSM_QUEUE tails (allocates that many bucket buffers on first use)
-  void set_pipelined(bool on);
+  // run every queued MSM on `st`; results are valid in stream order afterwards.  after_scatter
+  // (nullable) is recorded once the scalars have been read for the last time (uploads into the same
+  // staging buffers may then proceed).
+  void join(cudaStream_t st, cudaEvent_t after_scatter = nullptr);
+  // pipelined = queue up to `depth` MSMs per join (allocates the buffers for that many on first use);
+  // depth 0 = the default depth (ZKB200_QUEUE, 32), at most MSM_QUEUE
+  void set_pipelined(bool on, int depth = 0);
   void ensure_queue(int slots);
   // forget every queued tail (after an error between run() and join(): the queued output pointers
   // may refer to buffers that are being unwound); the caller drains the streams first
@@ -615,12 +637,18 @@ struct BaseTable {
     queued = 0;
     if (counts.p) cudaMemset(counts.p, 0, counts.bytes());   // a run cut short may have left the histogram dirty
   }
-  // stage timing (bench.py's roofline leg): when `profile` is set, run() brackets its stages with
-  // CUDA events; stage_ms() reads them after the streams have drained.
+  // stage timing (bench.py's roofline leg): when `profile` is set, every join brackets its stages
+  // with CUDA events (a ring of PROF_RING joins); stage_ms() / stage_totals() read them after the
+  // streams have drained.
   // stages: 0 digits+scan+scatter, 1 accumulate, 2 partial fix-up + bucket reduce, 3 combine+finalize
+  static constexpr int PROF_RING = 64;
+  struct ProfRec { cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; int msms = 0; };
   bool profile = false;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  void stage_ms(float out[4]);
+  std::vector<ProfRec> prof;   // allocated when profiling is first switched on
+  uint64_t prof_joins = 0;     // joins recorded since profiling was switched on
+  void set_profile(bool on);
+  void stage_ms(float out[4]);                                        // the last profiled join
+  void stage_totals(float out[4], uint64_t* msms, uint64_t* joins);   // sums over the recorded joins
   ~BaseTable();
   size_t device_bytes() const;
 };
@@ -636,8 +664,9 @@ struct PipelineScope {
   bool was;
   int exc, ctx;
   cudaStream_t extra;
-  PipelineScope(BaseTable<T>& t_, int ctx_, cudaStream_t extra_ = nullptr)
-      : t(t_), was(t_.pipelined), exc(std::uncaught_exceptions()), ctx(ctx_), extra(extra_) { t.set_pipelined(true); }
+  // depth = tails the scope will queue before it joins (a proof knows: 2 for Groth16's A and C)
+  PipelineScope(BaseTable<T>& t_, int ctx_, cudaStream_t extra_ = nullptr, int depth = 0)
+      : t(t_), was(t_.pipelined), exc(std::uncaught_exceptions()), ctx(ctx_), extra(extra_) { t.set_pipelined(true, depth); }
   PipelineScope(const PipelineScope&) = delete;
   PipelineScope& operator=(const PipelineScope&) = delete;
   ~PipelineScope() {

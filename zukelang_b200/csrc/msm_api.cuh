@@ -6,28 +6,29 @@
 namespace zk {
 
 // Staging of zk_g*_table_msm_batch, owned by the handle: nothing is allocated, created or freed
-// per call (round 1 paid three cudaMalloc, four cudaEventCreate and three device-synchronising
-// cudaFree inside the timed call).
+// per call once the ring has its size (round 1 paid three cudaMalloc, four cudaEventCreate and three
+// device-synchronising cudaFree inside the timed call).  One scalar buffer per queued MSM: a group
+// of MSMs is uploaded on the copy stream while the previous group is being accumulated.
 constexpr int BATCH_TIMED_STEPS = 64;
 struct BatchStage {
-  DevBuf<uint32_t> d_sc[2];              // double-buffered scalar vectors
+  std::vector<DevBuf<uint32_t>> d_sc;    // ring of scalar vectors, one per MSM of a group
   cudaStream_t copy = nullptr;           // upload stream
-  cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
-  // per-step timing (zk_table_batch_timing): upload start / end on the copy stream, first kernel /
-  // last kernel of the step on the compute stream
+  cudaEvent_t copied = nullptr;          // copy stream: the current group is on the device
+  cudaEvent_t scattered = nullptr;       // compute stream: the current group's scalars have been read for the last time
+  // per-step timing (zk_table_batch_timing): upload start / end on the copy stream; first / last kernel
+  // of the step's GROUP on the compute stream
   bool timed = false;
   int steps_timed = 0;
+  int group_of[BATCH_TIMED_STEPS] = {};
   cudaEvent_t t_c0[BATCH_TIMED_STEPS] = {}, t_c1[BATCH_TIMED_STEPS] = {}, t_k0[BATCH_TIMED_STEPS] = {},
               t_k1[BATCH_TIMED_STEPS] = {};
-  void ensure(size_t n) {
-    d_sc[0].ensure(n * 8);
-    d_sc[1].ensure(n * 8);
+  void ensure(size_t n, int depth) {
+    if ((int)d_sc.size() < depth) d_sc.resize(depth);
+    for (int i = 0; i < depth; i++) d_sc[i].ensure(n * 8);
     if (!copy) {
       ZK_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
-      for (int b = 0; b < 2; b++) {
-        ZK_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-        ZK_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
-      }
+      ZK_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+      ZK_CUDA(cudaEventCreateWithFlags(&scattered, cudaEventDisableTiming));
     }
     if (timed && !t_c0[0])
       for (int i = 0; i < BATCH_TIMED_STEPS; i++) {
@@ -37,7 +38,8 @@ struct BatchStage {
   }
   ~BatchStage() {
     if (copy) cudaStreamDestroy(copy);
-    for (int b = 0; b < 2; b++) { if (copied[b]) cudaEventDestroy(copied[b]); if (consumed[b]) cudaEventDestroy(consumed[b]); }
+    if (copied) cudaEventDestroy(copied);
+    if (scattered) cudaEventDestroy(scattered);
     if (t_c0[0])
       for (int i = 0; i < BATCH_TIMED_STEPS; i++) {
         cudaEventDestroy(t_c0[i]); cudaEventDestroy(t_c1[i]); cudaEventDestroy(t_k0[i]); cudaEventDestroy(t_k1[i]);
@@ -179,9 +181,11 @@ int api_table_msm(uint64_t handle, const uint8_t* scalars, size_t n, uint8_t* ou
   ZK_API_END
 }
 
-// `count` MSMs over the same table with host scalars: on every device the uploads are
-// double-buffered on a copy stream so that H2D of MSM i+1 overlaps the accumulation of MSM i, and
-// the tails are batched.
+// `count` MSMs over the same table with host scalars, in groups: on every device a group's scalar
+// vectors are uploaded on a copy stream (into one staging buffer per MSM) while the previous group
+// is being accumulated, then the group is queued and joined: ONE sort, accumulation and tail for
+// the whole group.  The first group is short — about 100 MB of scalars, so that the computation
+// starts after ~2 ms of uploads — the following ones take the queue depth.
 template <class T>
 int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n, size_t count, uint8_t* out) {
   ZK_API_BEGIN
@@ -197,44 +201,64 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
   if (multi) h->d_gather.ensure(count * (size_t)active);
   ZK_CUDA(cudaMemsetAsync(h->d_err.p, 0, sizeof(int), st0));
   ZK_CUDA(cudaEventRecord(h->ready, st0));
-  // pipelined for the call; on unwind every device is drained and the queued tails are dropped
+  // pipelined for the call; on unwind every device is drained and the queue is dropped
   std::vector<std::unique_ptr<PipelineScope<T>>> scopes;
+  int depth = MSM_QUEUE;
+  for (int p = 0; p < active; p++) {
+    TablePart<T>& P = *h->parts[p];
+    CtxScope scope(P.ctx);
+    if (!P.batch.copy) P.batch.ensure(0, 0);                     // the copy stream, for the scope below
+    scopes.push_back(std::make_unique<PipelineScope<T>>(P.table, P.ctx, P.batch.copy));
+    depth = std::min(depth, P.table.queue_cap);
+  }
+  depth = (int)std::min<size_t>((size_t)depth, count);
+  size_t widest = 0;
   for (int p = 0; p < active; p++) {
     TablePart<T>& P = *h->parts[p];
     CtxScope scope(P.ctx);
     const uint32_t cnt = (uint32_t)std::min<size_t>(n, (size_t)P.lo + P.table.n) - P.lo;
-    P.batch.ensure(cnt);
-    scopes.push_back(std::make_unique<PipelineScope<T>>(P.table, P.ctx, P.batch.copy));
+    widest = std::max<size_t>(widest, cnt);
+    P.batch.ensure(cnt, depth);
     P.batch.steps_timed = 0;
     if (multi) ZK_CUDA(cudaStreamWaitEvent(stream_of(P.ctx), h->ready, 0));
   }
-  for (size_t i = 0; i < count; i++) {
-    const int b = (int)(i & 1);
-    for (int p = 0; p < active; p++) {     // the host thread interleaves the devices step by step
+  const size_t first_group = std::min<size_t>((size_t)depth, std::max<size_t>(2, (100u << 20) / (widest * 32)));
+  int group_id = 0;
+  for (size_t g0 = 0; g0 < count; group_id++) {
+    const size_t g1 = std::min(count, g0 + (g0 == 0 ? first_group : (size_t)depth));
+    for (int p = 0; p < active; p++) {     // the host thread interleaves the devices group by group
       TablePart<T>& P = *h->parts[p];
       BatchStage& B = P.batch;
       CtxScope scope(P.ctx);
       cudaStream_t st = stream_of(P.ctx), cs = B.copy;
       const uint32_t cnt = (uint32_t)std::min<size_t>(n, (size_t)P.lo + P.table.n) - P.lo;
-      const bool tm = B.timed && i < (size_t)BATCH_TIMED_STEPS;
-      if (i >= 2) ZK_CUDA(cudaStreamWaitEvent(cs, B.consumed[b], 0));
-      if (tm) ZK_CUDA(cudaEventRecord(B.t_c0[i], cs));
-      ZK_CUDA(cudaMemcpyAsync(B.d_sc[b].p, scalars[i] + (size_t)P.lo * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, cs));
-      if (tm) ZK_CUDA(cudaEventRecord(B.t_c1[i], cs));
-      ZK_CUDA(cudaEventRecord(B.copied[b], cs));
-      ZK_CUDA(cudaStreamWaitEvent(st, B.copied[b], 0));
-      if (tm) ZK_CUDA(cudaEventRecord(B.t_k0[i], st));
-      // (the canonical-scalar check rides in the first digit pass)
-      if (multi) P.table.run(B.d_sc[b].p, cnt, h->d_gather.p + i * active + p, nullptr, st, 0, h->d_err.p);
-      else P.table.run(B.d_sc[b].p, cnt, nullptr, h->d_out.p + i * OUT, st, 0, h->d_err.p);
-      ZK_CUDA(cudaEventRecord(B.consumed[b], st));
-      if (tm) { ZK_CUDA(cudaEventRecord(B.t_k1[i], st)); B.steps_timed = (int)i + 1; }
+      if (g0 > 0) ZK_CUDA(cudaStreamWaitEvent(cs, B.scattered, 0));   // the staging ring is free again
+      for (size_t i = g0; i < g1; i++) {
+        const bool tm = B.timed && i < (size_t)BATCH_TIMED_STEPS;
+        if (tm) ZK_CUDA(cudaEventRecord(B.t_c0[i], cs));
+        ZK_CUDA(cudaMemcpyAsync(B.d_sc[i - g0].p, scalars[i] + (size_t)P.lo * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, cs));
+        if (tm) ZK_CUDA(cudaEventRecord(B.t_c1[i], cs));
+      }
+      ZK_CUDA(cudaEventRecord(B.copied, cs));
+      ZK_CUDA(cudaStreamWaitEvent(st, B.copied, 0));
+      const bool tmg = B.timed && g0 < (size_t)BATCH_TIMED_STEPS;
+      if (tmg) ZK_CUDA(cudaEventRecord(B.t_k0[g0], st));
+      for (size_t i = g0; i < g1; i++) {
+        // (the canonical-scalar check rides in the first digit pass)
+        if (multi) P.table.run(B.d_sc[i - g0].p, cnt, h->d_gather.p + i * active + p, nullptr, st, 0, h->d_err.p);
+        else P.table.run(B.d_sc[i - g0].p, cnt, nullptr, h->d_out.p + i * OUT, st, 0, h->d_err.p);
+      }
+      P.table.join(st, B.scattered);
+      if (tmg) {
+        ZK_CUDA(cudaEventRecord(B.t_k1[g0], st));
+        for (size_t i = g0; i < g1 && i < (size_t)BATCH_TIMED_STEPS; i++) { B.group_of[i] = (int)g0; B.steps_timed = (int)i + 1; }
+      }
     }
+    g0 = g1;
   }
   for (int p = 0; p < active; p++) {
     TablePart<T>& P = *h->parts[p];
     CtxScope scope(P.ctx);
-    P.table.join(stream_of(P.ctx));
     if (multi) ZK_CUDA(cudaEventRecord(P.done, stream_of(P.ctx)));
   }
   if (multi) {
@@ -252,8 +276,9 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
 }
 
 // Per-step timing of the last zk_g*_table_msm_batch on this handle (enable before the call):
-// out[4 i + 0] = upload start, [1] = upload end, [2] = first kernel, [3] = last kernel of step i,
-// in ms since the first upload started (first device's part).  *steps = steps written.
+// out[4 i + 0] = upload start, [1] = upload end of step i, [2] = first kernel, [3] = last kernel of
+// the GROUP step i was joined in, in ms since the first upload started (first device's part).
+// *steps = steps written.
 template <class T>
 int api_table_batch_timing(TableHandle<T>* h, int enable, float* out, size_t cap, size_t* steps) {
   BatchStage& B = h->parts[0]->batch;
@@ -262,8 +287,8 @@ int api_table_batch_timing(TableHandle<T>* h, int enable, float* out, size_t cap
     for (size_t i = 0; i < k; i++) {
       ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 0], B.t_c0[0], B.t_c0[i]));
       ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 1], B.t_c0[0], B.t_c1[i]));
-      ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 2], B.t_c0[0], B.t_k0[i]));
-      ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 3], B.t_c0[0], B.t_k1[i]));
+      ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 2], B.t_c0[0], B.t_k0[B.group_of[i]]));   // the step's group
+      ZK_CUDA(cudaEventElapsedTime(&out[4 * i + 3], B.t_c0[0], B.t_k1[B.group_of[i]]));
     }
     *steps = k;
   }

@@ -91,11 +91,6 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
     ZK_CUDA(cudaGetLastError());
     ZK_CUDA(cudaStreamSynchronize(st));
   }
-  uint32_t nb = cfg.nbuckets();
-  counts.alloc(nb);
-  cursor.alloc(nb);
-  tile_sums.alloc(cdiv(nb, SCAN_TILE) + 1);
-  entries.alloc((size_t)n * cfg.W);
   {
     // 9 (default): mixed add with paired products + cp.async staging, 2 blocks/SM; 8: paired, direct
     // loads; 5: plain mixed add + staging; 4: plain, direct loads, 2 blocks/SM; 1: plain, 4 blocks/SM
@@ -107,9 +102,9 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
     if (per_sm < 1) per_sm = 1;
     acc_blocks = (uint32_t)per_sm * (uint32_t)sm_count();
   }
-  ZK_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes(), st));   // kept zero between MSMs by k_scan_apply
-  partial_stride = 2 * (size_t)acc_blocks * ACC_THREADS;
-  heavy_stride = (size_t)acc_blocks * ACC_THREADS / 4 + 2;
+  // partial pieces and heavy-bucket queue of ONE accumulation launch (whatever the number of MSMs in it)
+  partial.alloc(2 * (size_t)acc_blocks * ACC_THREADS);
+  heavy.alloc((size_t)acc_blocks * ACC_THREADS / 4 + 2);
   queued = 0;
   queue_cap = 0;
   pipelined = false;
@@ -118,38 +113,21 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   ZK_CUDA(cudaStreamSynchronize(st));
 }
 
+// Queues one MSM; a table that is not pipelined runs it at once.
 template <class T>
 void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_result, uint8_t* d_out_bytes,
                        cudaStream_t st, uint32_t first, int* d_err) {
   ZK_REQUIRE(count > 0 && (uint64_t)first + count <= n, ZK_EARG, "scalar range exceeds the base table");
-  const uint32_t nb = cfg.nbuckets();
+  ZK_REQUIRE(d_scalars, ZK_EARG, "null scalar vector");
   if (queued >= queue_cap) join(st);
   const int slot = queued;
-  if (profile && !ev[0])
-    for (auto& e : ev) ZK_CUDA(cudaEventCreate(&e));
-  auto mark = [&](int i) { if (profile) ZK_CUDA(cudaEventRecord(ev[i], st)); };
-  // ---- sort and accumulate: five launches, no memsets (the histogram comes back zeroed) ----------
-  mark(0);
-  uint32_t* off = offsets.p + (size_t)slot * (nb + 1);
-  k_digits<false><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, first, n, cfg, counts.p, nullptr, d_err);
-  uint32_t ntiles = cdiv(nb, SCAN_TILE);
-  k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p);
-  k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nb, tile_sums.p, off, cursor.p);
-  k_digits<true><<<cdiv(count, 256), 256, 0, st>>>(d_scalars, skip.p, count, first, n, cfg, cursor.p, entries.p, nullptr);
-  mark(1);
-  // one wave at most; for small inputs fewer blocks, so that a slice still holds >= 16 entries
-  // (otherwise the partial fix-up, not the mixed adds, would end up doing the additions)
-  uint32_t grid = cdiv((uint64_t)count * cfg.W, 16 * ACC_THREADS);
-  if (grid > acc_blocks) grid = acc_blocks;
-  if (grid < 1) grid = 1;
-  acc_launch(grid, off, bucket_sums.p + (size_t)slot * nb, partial.p + (size_t)slot * partial_stride, st);
-  slot_geom.T[slot] = grid * ACC_THREADS;
-  mark(2);
-  // ---- queue the tail (partial fix-up, bucket reduction, window combine, wire bytes) -------------
+  slots.scalars[slot] = d_scalars;
+  slots.err[slot] = d_err;
+  slots.count[slot] = count;
+  slots.first[slot] = first;
   outs.result[slot] = d_result ? d_result : window_sums.p + (size_t)slot * (cfg.nwb + 1) + cfg.nwb;
   outs.bytes[slot] = d_out_bytes;
   queued++;
-  ZK_CUDA(cudaGetLastError());
   if (!pipelined) join(st);
 }
 
@@ -176,22 +154,32 @@ int BaseTable<T>::acc_occupancy() {
   return per_sm;
 }
 template <class T>
-void BaseTable<T>::acc_launch(uint32_t grid, const uint32_t* off, XYZZ<F>* bsum, XYZZ<F>* part, cudaStream_t st) {
+void BaseTable<T>::acc_launch(uint32_t grid, uint32_t nbuckets, cudaStream_t st) {
   acc_dispatch([&](auto kern, size_t smem) {
-    kern<<<grid, ACC_THREADS, smem, st>>>(pts.p, entries.p, off, bsum, part, cfg.nbuckets());
+    kern<<<grid, ACC_THREADS, smem, st>>>(pts.p, entries.p, offsets.p, bucket_sums.p, partial.p, nbuckets, (uint32_t)pts.n);
   });
 }
 
 template <class T>
 void BaseTable<T>::ensure_queue(int slots) {
+  // the queued MSMs are sorted and accumulated as ONE entry list: keep it below 2^29 entries
+  // (2 GB of point indices; entry positions are 32-bit)
+  const uint64_t per_msm = (uint64_t)n * cfg.W;
+  const int most = (int)std::max<uint64_t>(1, (1ull << 29) / per_msm);
+  slots = std::max(1, std::min(std::min(slots, most), MSM_QUEUE));
   if (slots <= queue_cap) return;
-  ZK_REQUIRE(queued == 0, ZK_EARG, "cannot resize the tail queue while MSMs are queued");
+  ZK_REQUIRE(queued == 0, ZK_EARG, "cannot resize the queue while MSMs are queued");
   const uint32_t nb = cfg.nbuckets();
+  const size_t nbq = (size_t)slots * nb;
   const uint32_t cpw = cfg.B / cfg.L;
-  bucket_sums.alloc((size_t)slots * nb);
-  offsets.alloc((size_t)slots * (nb + 1));
-  partial.alloc((size_t)slots * partial_stride);
-  heavy.alloc((size_t)slots * heavy_stride);
+  counts.alloc(nbq);
+  ZK_CUDA(cudaMemset(counts.p, 0, counts.bytes()));   // kept zero between joins by k_scan_apply
+  ZK_CUDA(cudaDeviceSynchronize());
+  cursor.alloc(nbq);
+  tile_sums.alloc(cdiv(nbq, SCAN_TILE) + 1);
+  offsets.alloc(nbq + 1);
+  entries.alloc((size_t)slots * per_msm);
+  bucket_sums.alloc(nbq);
   chunk_out.alloc((size_t)slots * cfg.nwb * cpw);
   tree_tmp.alloc((size_t)slots * cfg.nwb * cdiv(cpw, TAIL_THREADS) + 1);
   window_sums.alloc((size_t)slots * (cfg.nwb + 1));
@@ -199,32 +187,64 @@ void BaseTable<T>::ensure_queue(int slots) {
 }
 
 template <class T>
-void BaseTable<T>::set_pipelined(bool on) {
-  if (on) ensure_queue(MSM_QUEUE);
+void BaseTable<T>::set_pipelined(bool on, int depth) {
+  if (on) {
+    if (depth <= 0) depth = env_int("ZKB200_QUEUE", MSM_QUEUE);
+    if (queued == 0) ensure_queue(depth);   // cannot grow under queued MSMs: the current depth stays
+  }
   pipelined = on;
 }
 
-// Batched tail of every queued MSM: bucket reduction, window combine, affine conversion.
+// Everything queued, as one launch sequence: sort and accumulate all Q MSMs over Q * nb buckets, then
+// the batched tail (partial fix-up, bucket reduction, window combine, affine conversion).
 template <class T>
-void BaseTable<T>::join(cudaStream_t st) {
-  if (queued == 0) return;
+void BaseTable<T>::join(cudaStream_t st, cudaEvent_t after_scatter) {
+  if (queued == 0) {
+    if (after_scatter) ZK_CUDA(cudaEventRecord(after_scatter, st));
+    return;
+  }
   const uint32_t nb = cfg.nbuckets();
   const int Q = queued;
-  // chunk width of the running-sum reduction: narrow (shallow dependency chain) for a single MSM,
-  // wide (fewer per-chunk scalar multiplications, 3.3 instead of 7.3 additions per bucket) when the
-  // latency is shared by a batch
+  const uint32_t nbq = (uint32_t)Q * nb;
+  ProfRec* rec = nullptr;
+  if (profile) {
+    rec = &prof[prof_joins % PROF_RING];
+    rec->msms = Q;
+    prof_joins++;
+  }
+  auto mark = [&](int i) { if (rec) ZK_CUDA(cudaEventRecord(rec->ev[i], st)); };
+  uint32_t most = 0;
+  uint64_t total = 0;
+  for (int q = 0; q < Q; q++) { most = std::max(most, slots.count[q]); total += (uint64_t)slots.count[q] * cfg.W; }
+  // ---- sort: five launches for all Q MSMs, no memsets (the histogram comes back zeroed) -----------
+  mark(0);
+  k_digits<false><<<dim3(cdiv(most, 256), Q), 256, 0, st>>>(slots, skip.p, n, cfg, counts.p, nullptr, 0);
+  const uint32_t ntiles = cdiv(nbq, SCAN_TILE);
+  k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nbq, tile_sums.p);
+  k_scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(counts.p, nbq, tile_sums.p, offsets.p, cursor.p);
+  k_digits<true><<<dim3(cdiv(most, 256), Q), 256, 0, st>>>(slots, skip.p, n, cfg, cursor.p, entries.p, (uint32_t)entries.n);
+  if (after_scatter) ZK_CUDA(cudaEventRecord(after_scatter, st));
+  mark(1);
+  // ---- accumulate: one wave at most; for small inputs fewer blocks, so that a slice still holds
+  // >= 16 entries (otherwise the partial fix-up, not the mixed adds, would end up doing the additions)
+  uint32_t grid = (uint32_t)std::min<uint64_t>(acc_blocks, cdiv(total, (uint64_t)16 * ACC_THREADS));
+  if (grid < 1) grid = 1;
+  acc_launch(grid, nbq, st);
+  const uint32_t acc_threads = grid * ACC_THREADS;
+  mark(2);
+  // ---- tail: buckets that were split over several accumulation slices ...
+  ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));   // heavy[0] = 0
+  k_fix_partials<F><<<cdiv(nbq, 128), 128, 0, st>>>(offsets.p, bucket_sums.p, partial.p, nbq, acc_threads, heavy.p);
+  {
+    const int ht = sizeof(XYZZ<F>) > 192 ? 128 : 256;   // 48 KB of shared memory either way
+    k_fix_heavy<F><<<sm_count(), ht, ht * sizeof(XYZZ<F>), st>>>(offsets.p, bucket_sums.p, partial.p, nbq, acc_threads, heavy.p);
+  }
+  // ... bucket reduction.  Chunk width of the running sum: narrow (shallow dependency chain) for a
+  // single MSM, wide (fewer per-chunk scalar multiplications, 3.3 instead of 7.3 additions per
+  // bucket) when the latency is shared by a batch
   MsmConfig rc = cfg;
   if (Q >= 3 && env_int("ZKB200_REDUCE_CHUNK", 0) <= 0) { rc.L = 16; while ((uint32_t)rc.L > rc.B) rc.L >>= 1; }
   const uint32_t cpw = rc.B / rc.L;
-  // deferred fix-up of the buckets that were split over several accumulation slices, all queued MSMs at once
-  ZK_CUDA(cudaMemset2DAsync(heavy.p, heavy_stride * sizeof(uint32_t), 0, sizeof(uint32_t), Q, st));   // heavy[z][0] = 0
-  k_fix_partials<F><<<dim3(cdiv(nb, 128), 1, Q), 128, 0, st>>>(offsets.p, bucket_sums.p, partial.p, nb, partial_stride, slot_geom,
-                                                               heavy.p, heavy_stride);
-  {
-    const int ht = sizeof(XYZZ<F>) > 192 ? 128 : 256;   // 48 KB of shared memory either way
-    k_fix_heavy<F><<<dim3(sm_count(), 1, Q), ht, ht * sizeof(XYZZ<F>), st>>>(offsets.p, bucket_sums.p, partial.p, nb, partial_stride,
-                                                                             slot_geom, heavy.p, heavy_stride);
-  }
   k_reduce_chunks<F><<<dim3(cdiv((size_t)cpw * cfg.nwb, TAIL_THREADS), 1, Q), TAIL_THREADS, 0, st>>>(bucket_sums.p, rc,
                                                                                                      chunk_out.p);
   {
@@ -248,25 +268,55 @@ void BaseTable<T>::join(cudaStream_t st) {
       which ^= 1;
     }
   }
-  if (profile) ZK_CUDA(cudaEventRecord(ev[3], st));
+  mark(3);
   k_combine_finalize<T><<<Q, 32, 0, st>>>(window_sums.p, cfg, outs);
-  if (profile) ZK_CUDA(cudaEventRecord(ev[4], st));
+  mark(4);
   ZK_CUDA(cudaGetLastError());
   queued = 0;
 }
 
 template <class T>
-void BaseTable<T>::stage_ms(float out[4]) {
-  for (int i = 0; i < 4; i++) {
-    out[i] = 0.f;
-    if (ev[0]) ZK_CUDA(cudaEventElapsedTime(&out[i], ev[i], ev[i + 1]));
+void BaseTable<T>::set_profile(bool on) {
+  if (on && prof.empty()) {
+    prof.resize(PROF_RING);
+    for (auto& r : prof)
+      for (auto& e : r.ev) ZK_CUDA(cudaEventCreate(&e));
   }
+  if (on && !profile) prof_joins = 0;
+  profile = on;
+}
+
+template <class T>
+void BaseTable<T>::stage_ms(float out[4]) {
+  for (int i = 0; i < 4; i++) out[i] = 0.f;
+  if (prof_joins == 0) return;
+  const ProfRec& r = prof[(prof_joins - 1) % PROF_RING];
+  for (int i = 0; i < 4; i++) ZK_CUDA(cudaEventElapsedTime(&out[i], r.ev[i], r.ev[i + 1]));
+}
+
+template <class T>
+void BaseTable<T>::stage_totals(float out[4], uint64_t* msms, uint64_t* joins) {
+  for (int i = 0; i < 4; i++) out[i] = 0.f;
+  const uint64_t cnt = std::min<uint64_t>(prof_joins, PROF_RING);
+  uint64_t m = 0;
+  for (uint64_t j = 0; j < cnt; j++) {
+    const ProfRec& r = prof[j];
+    for (int i = 0; i < 4; i++) {
+      float ms = 0.f;
+      ZK_CUDA(cudaEventElapsedTime(&ms, r.ev[i], r.ev[i + 1]));
+      out[i] += ms;
+    }
+    m += (uint64_t)r.msms;
+  }
+  *msms = m;
+  *joins = cnt;
 }
 
 template <class T>
 BaseTable<T>::~BaseTable() {
-  for (auto& e : ev)
-    if (e) cudaEventDestroy(e);
+  for (auto& r : prof)
+    for (auto& e : r.ev)
+      if (e) cudaEventDestroy(e);
 }
 
 template <class T>

@@ -54,7 +54,7 @@ __device__ __forceinline__ Fr raw_one() { Fr o = Fr::zero(); o.v[0] = 1; return 
 // Groth16
 // ======================================================================================
 struct G16Layout {
-  uint32_t n, ti_lo, ti_cnt, h_lo, h_cnt, mid_lo, mid_cnt;
+  uint32_t n, m, ti_lo, ti_cnt, h_lo, h_cnt, mid_lo, mid_cnt;
   int singles;  // 1 on the shard that owns a, b1, d1, b2, d2
 };
 
@@ -86,11 +86,17 @@ struct Groth16Key : HandleBase {
   DevBuf<uint8_t> d_out;
   cudaEvent_t ready = nullptr;
   cudaEvent_t t_begin = nullptr, t_end = nullptr;   // device time of the last prove (zk_groth16_last_device_ms)
+  // stage marks of the last prove on the primary device's stream (zk_groth16_last_stage_ms):
+  // 0 witness uploaded, 1 V | W | Y and h ready, 2 MSM scalars written, 3 A / 4 C / 5 B accumulated
+  // (primary device's part), 6 tails joined (primary part)
+  static constexpr int NMARK = 7;
+  cudaEvent_t mark[NMARK] = {};
   Groth16Key() { kind = 4; }
   ~Groth16Key() {
     if (ready) cudaEventDestroy(ready);
     if (t_begin) cudaEventDestroy(t_begin);
     if (t_end) cudaEventDestroy(t_end);
+    for (cudaEvent_t e : mark) if (e) cudaEventDestroy(e);
   }
 };
 
@@ -118,8 +124,10 @@ k_groth16_scalars(G16Layout L, const Fr* __restrict__ vwy, const Fr* __restrict_
     put_raw(sC, 3 + t, c.from_mont());
   }
   if (t < L.h_cnt) put_raw(sC, 3 + (size_t)L.ti_cnt + t, load_vec_rw(&H[L.h_lo + t]).from_mont());
-  if (t < L.mid_cnt)
+  if (t < L.mid_cnt) {
+    ZK_DCHECK(mid_index[L.mid_lo + t] < L.m);
     put_raw(sC, 3 + (size_t)L.ti_cnt + L.h_cnt + t, get_raw(sol_raw, mid_index[L.mid_lo + t]));
+  }
 }
 
 }  // namespace zk
@@ -151,6 +159,7 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
     cudaStream_t st = stream_of(p);
     G16Layout& L = part->lay;
     L.n = (uint32_t)pk->n;
+    L.m = (uint32_t)pk->m;
     slice(pk->n, idx, cnt, &L.ti_lo, &L.ti_cnt);
     slice(pk->n_h ? pk->n_h : pk->n - 1, idx, cnt, &L.h_lo, &L.h_cnt);
     slice(pk->n_mid, idx, cnt, &L.mid_lo, &L.mid_cnt);
@@ -182,6 +191,7 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
   ZK_CUDA(cudaEventCreateWithFlags(&k->ready, cudaEventDisableTiming));
   ZK_CUDA(cudaEventCreate(&k->t_begin));
   ZK_CUDA(cudaEventCreate(&k->t_end));
+  for (cudaEvent_t& e : k->mark) ZK_CUDA(cudaEventCreate(&e));
   *handle = register_handle(std::move(k));
   ZK_API_END
 }
@@ -190,6 +200,7 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
 static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* flag, cudaStream_t st0, uint8_t* proof_out) {
   using namespace zk;
   const int np = (int)k->parts.size();
+  ZK_CUDA(cudaEventRecord(k->mark[1], st0));
   if (np > 1) ZK_CUDA(cudaEventRecord(k->ready, st0));
   for (int p = 0; p < np; p++) {
     Groth16Part& P = *k->parts[p];
@@ -201,22 +212,28 @@ static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* 
     // the scalars of this part's three MSMs, read from the primary device's V | W, h and witness
     k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, vwy, Hq, k->d_sol.p, P.mid_index.p, k->d_rs.p, P.sA.p,
                                                         P.qB.scalars.p, P.qC.scalars.p);
+    const bool primary = P.ctx == 0;
+    if (primary) ZK_CUDA(cudaEventRecord(k->mark[2], st));
     // tails (bucket reduction, affine conversion) of A and C overlap the next accumulation; an error
     // between run() and join() drains the device and drops the queued tails (PipelineScope)
-    PipelineScope<G1Traits> scope1(P.qC.table, P.ctx);
-    PipelineScope<G2Traits> scope2(P.qB.table, P.ctx);
+    PipelineScope<G1Traits> scope1(P.qC.table, P.ctx, nullptr, 2);
+    PipelineScope<G2Traits> scope2(P.qB.table, P.ctx, nullptr, 1);
     XYZZ<Fp>* rA = np > 1 ? k->g1.p + p : P.r1.p;
     XYZZ<Fp>* rC = np > 1 ? k->g1.p + np + p : P.r1.p + 1;
     XYZZ<Fp2>* rB = np > 1 ? k->g2.p + p : P.r2.p;
     uint8_t* o = np > 1 ? nullptr : k->d_out.p;       // one part: wire bytes straight from the tail
     P.qC.table.run(P.sA.p, 3 + L.ti_cnt, rA, o, st);                                                       // A
+    if (primary) ZK_CUDA(cudaEventRecord(k->mark[3], st));
     P.qC.table.run(P.qC.scalars.p, P.qC.table.n, rC, o ? o + ZK_G1_OUT + ZK_G2_OUT : nullptr, st);         // C
+    if (primary) ZK_CUDA(cudaEventRecord(k->mark[4], st));
     P.qB.table.run(P.qB.scalars.p, P.qB.table.n, rB, o ? o + ZK_G1_OUT : nullptr, st);                     // B
+    if (primary) ZK_CUDA(cudaEventRecord(k->mark[5], st));
     // all three accumulations are enqueued; the G2 tail runs on the auxiliary stream next to the G1 tail
     cudaStream_t aux = fork_aux(st);
     P.qB.table.join(aux);
     P.qC.table.join(st);
     join_aux(st);
+    if (primary) ZK_CUDA(cudaEventRecord(k->mark[6], st));
     if (np > 1) ZK_CUDA(cudaEventRecord(P.done, st));
   }
   if (np > 1) {
@@ -262,6 +279,7 @@ int zk_groth16_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* sol
   ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaEventRecord(k->mark[0], st));
   q.eval(k->d_sol.p, st);
   groth16_finish(k, q.Vc.p, q.H.p, q.flag.p, st, proof_out);
   ZK_API_END
@@ -286,6 +304,7 @@ int zk_groth16_prove_coeffs(uint64_t pk_handle, uint64_t qap_handle, const uint8
   ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaEventRecord(k->mark[0], st));
   q.set_coeffs(qh->d_raw.p, st);
   q.quotient_from_work(st);
   groth16_finish(k, q.Vc.p, q.H.p, q.flag.p, st, proof_out);
@@ -310,6 +329,7 @@ int zk_groth16_prove_r1cs(uint64_t pk_handle, uint64_t domain_handle, const uint
   ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaEventRecord(k->mark[0], st));
   d.eval(k->d_sol.p, st);
   groth16_finish(k, d.evals.p, d.H.p, d.flag.p, st, proof_out);
   ZK_API_END
@@ -324,6 +344,20 @@ int zk_groth16_last_device_ms(uint64_t pk_handle, float* ms) {
   auto* k = static_cast<Groth16Key*>(lookup_handle(pk_handle, 4));
   ZK_REQUIRE(ms, ZK_EARG, "groth16_last_device_ms: null argument");
   ZK_CUDA(cudaEventElapsedTime(ms, k->t_begin, k->t_end));
+  ZK_API_END
+}
+
+// Stage split of the last zk_groth16_prove* on this key, in ms (CUDA events on the primary device's
+// stream): [0] witness upload, [1] QAP evaluation + quotient h, [2] MSM scalars, [3] A, [4] C and
+// [5] B sorted + accumulated (the primary device's part), [6] batched tails of the three MSMs,
+// [7] wait for the other devices + combine + download.
+int zk_groth16_last_stage_ms(uint64_t pk_handle, float out[8]) {
+  ZK_API_BEGIN
+  using namespace zk;
+  auto* k = static_cast<Groth16Key*>(lookup_handle(pk_handle, 4));
+  ZK_REQUIRE(out, ZK_EARG, "groth16_last_stage_ms: null argument");
+  cudaEvent_t seq[9] = {k->t_begin, k->mark[0], k->mark[1], k->mark[2], k->mark[3], k->mark[4], k->mark[5], k->mark[6], k->t_end};
+  for (int i = 0; i < 8; i++) ZK_CUDA(cudaEventElapsedTime(&out[i], seq[i], seq[i + 1]));
   ZK_API_END
 }
 
@@ -503,8 +537,8 @@ int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* s
   uint8_t* o_waw = o;                      o += ZK_G2_OUT;
   uint8_t* o_yay = o;                      o += ZK_G1_OUT;
   uint8_t* o_bvwy = o;
-  PipelineScope<G1Traits> scope1(k->q1.table, k->ctx);
-  PipelineScope<G2Traits> scope2(k->q2.table, k->ctx);
+  PipelineScope<G1Traits> scope1(k->q1.table, k->ctx, nullptr, 6);
+  PipelineScope<G2Traits> scope2(k->q2.table, k->ctx, nullptr, 2);
   auto run1 = [&](int slot, uint8_t* out) { k->q1.table.run(at1(slot), k->cnt1[slot], nullptr, out, st, k->first1[slot]); };
   auto run2 = [&](int slot, uint8_t* out) { k->q2.table.run(at2(slot), k->cnt2[slot], nullptr, out, st, k->first2[slot]); };
   run1(0, o_vv); run1(1, o_yy); run1(5, o_h); run1(2, o_vav); run1(3, o_yay); run1(4, o_bvwy);
