@@ -407,7 +407,7 @@ def run_gpu_arm(args):
     outs_host = torch.zeros(args.steps, 144, dtype=torch.uint8).pin_memory()
     ptrs = (ctypes.c_void_p * args.steps)(*[batches[b]["host"].data_ptr() for b in slots])
     _lib.check(zk.zk_table_batch_timing(handle.value, 1, None, 0, None))
-    _lib.check(zk.zk_g1_table_msm_batch(handle.value, ptrs, n, min(2, args.steps), outs_host.data_ptr()))   # warm-up
+    _lib.check(zk.zk_g1_table_msm_batch(handle.value, ptrs, n, args.steps, outs_host.data_ptr()))   # warm-up (sizes the staging ring)
     gathered = torch.empty(world, args.steps, 96, dtype=torch.uint8, device="cuda")
     sums = torch.empty(args.steps, 144, dtype=torch.uint8, device="cuda")
     rep_s = []

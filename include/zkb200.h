@@ -243,8 +243,9 @@ typedef struct {
  * the last zk_groth16_prove* call on this key; for bench.py. */
 int zk_groth16_last_device_ms(uint64_t pk, float *ms);
 /* Stage split of that time, in ms: [0] witness upload, [1] QAP evaluation + quotient h(x),
- * [2] MSM scalars, [3] A, [4] C and [5] B sorted and accumulated (the primary device's part),
- * [6] batched tails of the three MSMs, [7] wait for the other devices + combine + download. */
+ * [2] MSM scalars, [3] counting sort of A and C (one entry list), [4] their accumulation (one
+ * launch), [5] B sorted and accumulated (the primary device's part), [6] tails of the G1 and G2
+ * MSMs side by side, [7] wait for the other devices + combine + download. */
 int zk_groth16_last_stage_ms(uint64_t pk, float out[8]);
 
 int zk_pinocchio_pk_load(const zk_pinocchio_pkey *pk, int shard_index, int shard_count, uint64_t *handle);

@@ -240,7 +240,7 @@ template <class F, int MINB, bool STAGED, bool PAIRED = false>
 __global__ void __launch_bounds__(ACC_THREADS, MINB)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ entries,
              const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums, XYZZ<F>* __restrict__ partial,
-             uint32_t nbuckets, uint32_t npoints) {
+             uint32_t* __restrict__ open_bucket, uint32_t nbuckets, uint32_t npoints) {
   extern __shared__ uint4 acc_stage[];   // [2][VEC][ACC_THREADS] when STAGED: conflict-free 16-byte columns
   constexpr int VEC = sizeof(Affine<F>) / 16;
   const uint32_t T = gridDim.x * blockDim.x;
@@ -248,7 +248,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
   const uint32_t E = offsets[nbuckets];
   const uint32_t per = (E + T - 1) / T;
   const uint64_t e0_64 = (uint64_t)t * per;
-  if (per == 0 || e0_64 >= E) return;
+  if (per == 0 || e0_64 >= E) { open_bucket[t] = 0xffffffffu; return; }
   const uint32_t e0 = (uint32_t)e0_64;
   const uint32_t e1 = min(E, e0 + per);
   auto issue = [&](int buf, uint32_t ent) {
@@ -321,26 +321,33 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
   const bool ends_here = e1 == b_end;
   if (starts_here && ends_here) store_vec(&bucket_sums[b], acc);
   else store_vec(&partial[2 * (size_t)t + (e0 >= offsets[b] ? 0 : 1)], acc);
+  // the bucket this slice stops inside of (it continues in slice t + 1), for k_fix_partials
+  open_bucket[t] = ends_here ? 0xffffffffu : b;
 }
 
-// Step 4b: one thread per bucket (all queued MSMs: nbuckets = Q * nb): empty buckets become the
-// identity; a bucket split over a few slices gets the sum of its pieces (slot rule as in
-// k_accumulate; T = threads the accumulation ran with).  Buckets split over more than HEAVY_PIECES
-// slices (skewed scalars) are queued for k_fix_heavy.
+// Step 4b: buckets split over several slices.  One thread per accumulation SLICE (not per bucket: the
+// split buckets are at most T of the Q * nb buckets, and a thread per bucket would run the addition
+// code with one or two live lanes per warp): slice t stopped inside bucket open_bucket[t]; the
+// thread of the slice the bucket STARTS in adds up its pieces (slot rule as in k_accumulate) — or
+// queues it for k_fix_heavy when it spans more than HEAVY_PIECES slices (skewed scalars, SURVEY.md
+// H4).  Empty buckets are never written: k_reduce_chunks reads them as the identity.
 constexpr uint32_t HEAVY_PIECES = 8;
 template <class F>
 __global__ void __launch_bounds__(128)
 k_fix_partials(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucket_sums,
-               const XYZZ<F>* __restrict__ partial, uint32_t nbuckets, uint32_t T, uint32_t* __restrict__ heavy) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbuckets) return;
+               const XYZZ<F>* __restrict__ partial, const uint32_t* __restrict__ open_bucket, uint32_t nbuckets, uint32_t T,
+               uint32_t* __restrict__ heavy) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint32_t b = open_bucket[t];
+  if (b == 0xffffffffu) return;
+  ZK_DCHECK(b < nbuckets);
   const uint32_t E = offsets[nbuckets];
-  const uint32_t lo = offsets[b], hi = offsets[b + 1];
-  if (lo == hi) { store_vec(&bucket_sums[b], XYZZ<F>::inf()); return; }
   const uint32_t per = (E + T - 1) / T;
+  const uint32_t lo = offsets[b], hi = offsets[b + 1];
   const uint32_t t_first = lo / per, t_last = (hi - 1) / per;
-  ZK_DCHECK(lo <= hi && hi <= E && t_last < T);
-  if (t_first == t_last) return;  // written whole by its slice
+  ZK_DCHECK(lo < hi && hi <= E && t_last < T && t_first <= t && t < t_last);
+  if (t_first != t) return;       // the bucket started in an earlier slice: that slice's thread owns it
   if (t_last - t_first + 1 > HEAVY_PIECES) {
     const uint32_t slot = atomicAdd(heavy, 1u);
     ZK_DCHECK(slot + 1 < T / 4 + 2);   // heavy queue capacity: a heavy bucket spans > 8 of the T slices
@@ -348,9 +355,9 @@ k_fix_partials(const uint32_t* __restrict__ offsets, XYZZ<F>* __restrict__ bucke
     return;
   }
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t t = t_first; t <= t_last; t++) {
-    const uint32_t slot = ((uint64_t)t * per >= lo) ? 0 : 1;
-    XYZZ<F> p = load_vec_rw(&partial[2 * (size_t)t + slot]);
+  for (uint32_t s = t_first; s <= t_last; s++) {
+    const uint32_t slot = ((uint64_t)s * per >= lo) ? 0 : 1;
+    XYZZ<F> p = load_vec_rw(&partial[2 * (size_t)s + slot]);
     acc.add(p);
   }
   store_vec(&bucket_sums[b], acc);
@@ -414,18 +421,25 @@ __device__ __noinline__ XYZZ<F> small_mul(const XYZZ<F>& p, uint32_t k) {
 constexpr int TAIL_THREADS = 64;
 template <class F>
 __global__ void __launch_bounds__(TAIL_THREADS)
-k_reduce_chunks(const XYZZ<F>* __restrict__ bucket_sums_all, MsmConfig cfg, XYZZ<F>* __restrict__ chunk_out_all) {
+k_reduce_chunks(const XYZZ<F>* __restrict__ bucket_sums_all, const uint32_t* __restrict__ offsets_all, MsmConfig cfg,
+                XYZZ<F>* __restrict__ chunk_out_all) {
   uint32_t chunks_per_window = cfg.B / cfg.L;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= chunks_per_window * (uint32_t)cfg.nwb) return;
   const XYZZ<F>* bucket_sums = bucket_sums_all + (size_t)blockIdx.z * cfg.nbuckets();       // z = queued MSM
+  const uint32_t* offsets = offsets_all + (size_t)blockIdx.z * cfg.nbuckets();
   XYZZ<F>* chunk_out = chunk_out_all + (size_t)blockIdx.z * chunks_per_window * cfg.nwb;
   uint32_t wb = t / chunks_per_window, ch = t % chunks_per_window;
   uint32_t first = wb * cfg.B + ch * cfg.L;
   XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+  uint32_t hi = offsets[first + cfg.L];
   for (int j = cfg.L - 1; j >= 0; j--) {
-    XYZZ<F> p = load_vec_rw(&bucket_sums[first + j]);
-    run.add(p);
+    const uint32_t lo = offsets[first + j];
+    if (lo != hi) {                       // an empty bucket was never written: it is the identity
+      XYZZ<F> p = load_vec_rw(&bucket_sums[first + j]);
+      run.add(p);
+    }
+    hi = lo;
     acc.add(run);
   }
   // acc = sum (j+1) * bucket_j ; run = sum bucket_j ; add (ch*L) * run
@@ -596,6 +610,7 @@ struct BaseTable {
   // for queue_cap queued MSMs: queued MSM q owns buckets [q * nb, (q + 1) * nb).
   DevBuf<uint32_t> counts, cursor, tile_sums, entries;   // counts is all zero between joins (k_scan_apply clears it)
   DevBuf<uint32_t> offsets, heavy;   // bucket offsets (queue_cap * nb + 1); heavy[0] = queue length, then the queue
+  DevBuf<uint32_t> open_bucket;      // per accumulation slice: the bucket it stopped inside of (or ~0)
   // Queued MSMs.  run() only records the MSM (scalar pointer, range, output slots); join() sorts,
   // accumulates and reduces everything queued with ONE launch sequence on the caller's stream: the
   // latency-bound end of an MSM (bucket reduction, window combine, affine conversion: ~40 dependent
@@ -609,6 +624,8 @@ struct BaseTable {
   int acc_occupancy();
   void acc_launch(uint32_t grid, uint32_t nbuckets, cudaStream_t st);
   int queued = 0;
+  int pending = 0;           // MSMs sorted and accumulated whose tail has not been enqueued yet
+  uint32_t pending_threads = 0;   // threads their accumulation ran with
   int queue_cap = 0;         // MSMs one join can take with the buffers currently allocated (1 unless pipelined)
   QueueSlots slots{};
   TailOutputs<F> outs{};
@@ -627,6 +644,12 @@ struct BaseTable {
   // (nullable) is recorded once the scalars have been read for the last time (uploads into the same
   // staging buffers may then proceed).
   void join(cudaStream_t st, cudaEvent_t after_scatter = nullptr);
+  // The two halves of join(), for callers that overlap the latency-bound tails of two tables on two
+  // streams (Groth16: G1 and G2): sort_accumulate() runs the throughput-bound part of everything
+  // queued, tail() the batched reduction of what sort_accumulate() left pending (any stream that is
+  // ordered after it).
+  void sort_accumulate(cudaStream_t st, cudaEvent_t after_scatter = nullptr);
+  void tail(cudaStream_t st);
   // pipelined = queue up to `depth` MSMs per join (allocates the buffers for that many on first use);
   // depth 0 = the default depth (ZKB200_QUEUE, 32), at most MSM_QUEUE
   void set_pipelined(bool on, int depth = 0);
@@ -635,6 +658,7 @@ struct BaseTable {
   // may refer to buffers that are being unwound); the caller drains the streams first
   void abort_queue() {
     queued = 0;
+    pending = 0;
     if (counts.p) cudaMemset(counts.p, 0, counts.bytes());   // a run cut short may have left the histogram dirty
   }
   // stage timing (bench.py's roofline leg): when `profile` is set, every join brackets its stages

@@ -184,8 +184,8 @@ int api_table_msm(uint64_t handle, const uint8_t* scalars, size_t n, uint8_t* ou
 // `count` MSMs over the same table with host scalars, in groups: on every device a group's scalar
 // vectors are uploaded on a copy stream (into one staging buffer per MSM) while the previous group
 // is being accumulated, then the group is queued and joined: ONE sort, accumulation and tail for
-// the whole group.  The first group is short — about 100 MB of scalars, so that the computation
-// starts after ~2 ms of uploads — the following ones take the queue depth.
+// the whole group.  The first group is short — just long enough to cover the upload of the rest —
+// the following ones take the queue depth.
 template <class T>
 int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n, size_t count, uint8_t* out) {
   ZK_API_BEGIN
@@ -222,7 +222,17 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
     P.batch.steps_timed = 0;
     if (multi) ZK_CUDA(cudaStreamWaitEvent(stream_of(P.ctx), h->ready, 0));
   }
-  const size_t first_group = std::min<size_t>((size_t)depth, std::max<size_t>(2, (100u << 20) / (widest * 32)));
+  // Size of the first group: large enough that its computation (s per MSM, plus one tail) covers the
+  // upload of everything after it (u per MSM), small enough that little upload time is exposed
+  // before the first kernel:  (count - g) u <= g s + tail.  u from 40 GB/s of pinned-host bandwidth,
+  // s from 0.38 ns per bucket addition, tail ~ 1.2 ms.
+  size_t first_group = 1;
+  {
+    const double u = (double)widest * 32 / 40e9, sdur = (double)widest * h->parts[0]->table.cfg.W * 0.38e-9, tail = 1.2e-3;
+    const double g = ((double)count * u - tail) / (sdur + u);
+    if (g > 1) first_group = (size_t)g + 1;
+    first_group = std::min<size_t>(first_group, (size_t)depth);
+  }
   int group_id = 0;
   for (size_t g0 = 0; g0 < count; group_id++) {
     const size_t g1 = std::min(count, g0 + (g0 == 0 ? first_group : (size_t)depth));

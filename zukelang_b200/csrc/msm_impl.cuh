@@ -105,6 +105,7 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   // partial pieces and heavy-bucket queue of ONE accumulation launch (whatever the number of MSMs in it)
   partial.alloc(2 * (size_t)acc_blocks * ACC_THREADS);
   heavy.alloc((size_t)acc_blocks * ACC_THREADS / 4 + 2);
+  open_bucket.alloc((size_t)acc_blocks * ACC_THREADS);
   queued = 0;
   queue_cap = 0;
   pipelined = false;
@@ -119,6 +120,7 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
                        cudaStream_t st, uint32_t first, int* d_err) {
   ZK_REQUIRE(count > 0 && (uint64_t)first + count <= n, ZK_EARG, "scalar range exceeds the base table");
   ZK_REQUIRE(d_scalars, ZK_EARG, "null scalar vector");
+  if (pending) tail(st);              // a sort_accumulate() whose tail was never asked for
   if (queued >= queue_cap) join(st);
   const int slot = queued;
   slots.scalars[slot] = d_scalars;
@@ -156,7 +158,7 @@ int BaseTable<T>::acc_occupancy() {
 template <class T>
 void BaseTable<T>::acc_launch(uint32_t grid, uint32_t nbuckets, cudaStream_t st) {
   acc_dispatch([&](auto kern, size_t smem) {
-    kern<<<grid, ACC_THREADS, smem, st>>>(pts.p, entries.p, offsets.p, bucket_sums.p, partial.p, nbuckets, (uint32_t)pts.n);
+    kern<<<grid, ACC_THREADS, smem, st>>>(pts.p, entries.p, offsets.p, bucket_sums.p, partial.p, open_bucket.p, nbuckets, (uint32_t)pts.n);
   });
 }
 
@@ -199,6 +201,13 @@ void BaseTable<T>::set_pipelined(bool on, int depth) {
 // the batched tail (partial fix-up, bucket reduction, window combine, affine conversion).
 template <class T>
 void BaseTable<T>::join(cudaStream_t st, cudaEvent_t after_scatter) {
+  sort_accumulate(st, after_scatter);
+  tail(st);
+}
+
+template <class T>
+void BaseTable<T>::sort_accumulate(cudaStream_t st, cudaEvent_t after_scatter) {
+  if (pending) tail(st);
   if (queued == 0) {
     if (after_scatter) ZK_CUDA(cudaEventRecord(after_scatter, st));
     return;
@@ -230,22 +239,37 @@ void BaseTable<T>::join(cudaStream_t st, cudaEvent_t after_scatter) {
   uint32_t grid = (uint32_t)std::min<uint64_t>(acc_blocks, cdiv(total, (uint64_t)16 * ACC_THREADS));
   if (grid < 1) grid = 1;
   acc_launch(grid, nbq, st);
-  const uint32_t acc_threads = grid * ACC_THREADS;
   mark(2);
-  // ---- tail: buckets that were split over several accumulation slices ...
+  ZK_CUDA(cudaGetLastError());
+  pending = Q;
+  pending_threads = grid * ACC_THREADS;
+  queued = 0;
+}
+
+template <class T>
+void BaseTable<T>::tail(cudaStream_t st) {
+  if (pending == 0) return;
+  const uint32_t nb = cfg.nbuckets();
+  const int Q = pending;
+  const uint32_t nbq = (uint32_t)Q * nb;
+  const uint32_t acc_threads = pending_threads;
+  ProfRec* rec = profile && prof_joins ? &prof[(prof_joins - 1) % PROF_RING] : nullptr;
+  auto mark = [&](int i) { if (rec) ZK_CUDA(cudaEventRecord(rec->ev[i], st)); };
+  // ---- buckets that were split over several accumulation slices ...
   ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));   // heavy[0] = 0
-  k_fix_partials<F><<<cdiv(nbq, 128), 128, 0, st>>>(offsets.p, bucket_sums.p, partial.p, nbq, acc_threads, heavy.p);
+  k_fix_partials<F><<<cdiv(acc_threads, 128), 128, 0, st>>>(offsets.p, bucket_sums.p, partial.p, open_bucket.p, nbq, acc_threads, heavy.p);
   {
     const int ht = sizeof(XYZZ<F>) > 192 ? 128 : 256;   // 48 KB of shared memory either way
     k_fix_heavy<F><<<sm_count(), ht, ht * sizeof(XYZZ<F>), st>>>(offsets.p, bucket_sums.p, partial.p, nbq, acc_threads, heavy.p);
   }
   // ... bucket reduction.  Chunk width of the running sum: narrow (shallow dependency chain) for a
-  // single MSM, wide (fewer per-chunk scalar multiplications, 3.3 instead of 7.3 additions per
-  // bucket) when the latency is shared by a batch
+  // single MSM, wider (fewer per-chunk scalar multiplications: 3.3 additions per bucket at L = 16 and
+  // 2.7 at L = 32, against 7.3 at L = 4) once the latency is shared by a batch — a batch of 8 or more
+  // keeps the machine busy with half as many threads, and then the work is what counts
   MsmConfig rc = cfg;
-  if (Q >= 3 && env_int("ZKB200_REDUCE_CHUNK", 0) <= 0) { rc.L = 16; while ((uint32_t)rc.L > rc.B) rc.L >>= 1; }
+  if (Q >= 3 && env_int("ZKB200_REDUCE_CHUNK", 0) <= 0) { rc.L = Q >= 8 ? 32 : 16; while ((uint32_t)rc.L > rc.B) rc.L >>= 1; }
   const uint32_t cpw = rc.B / rc.L;
-  k_reduce_chunks<F><<<dim3(cdiv((size_t)cpw * cfg.nwb, TAIL_THREADS), 1, Q), TAIL_THREADS, 0, st>>>(bucket_sums.p, rc,
+  k_reduce_chunks<F><<<dim3(cdiv((size_t)cpw * cfg.nwb, TAIL_THREADS), 1, Q), TAIL_THREADS, 0, st>>>(bucket_sums.p, offsets.p, rc,
                                                                                                      chunk_out.p);
   {
     // sum tree per (window, queued MSM): cpw -> ceil(cpw / TAIL_THREADS) -> ... -> 1
@@ -272,7 +296,7 @@ void BaseTable<T>::join(cudaStream_t st, cudaEvent_t after_scatter) {
   k_combine_finalize<T><<<Q, 32, 0, st>>>(window_sums.p, cfg, outs);
   mark(4);
   ZK_CUDA(cudaGetLastError());
-  queued = 0;
+  pending = 0;
 }
 
 template <class T>

@@ -87,8 +87,8 @@ struct Groth16Key : HandleBase {
   cudaEvent_t ready = nullptr;
   cudaEvent_t t_begin = nullptr, t_end = nullptr;   // device time of the last prove (zk_groth16_last_device_ms)
   // stage marks of the last prove on the primary device's stream (zk_groth16_last_stage_ms):
-  // 0 witness uploaded, 1 V | W | Y and h ready, 2 MSM scalars written, 3 A / 4 C / 5 B accumulated
-  // (primary device's part), 6 tails joined (primary part)
+  // 0 witness uploaded, 1 V | W | Y and h ready, 2 MSM scalars written, 3 A and C sorted, 4 A and C
+  // accumulated, 5 B sorted and accumulated (primary device's part), 6 tails joined (primary part)
   static constexpr int NMARK = 7;
   cudaEvent_t mark[NMARK] = {};
   Groth16Key() { kind = 4; }
@@ -214,24 +214,26 @@ static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* 
                                                         P.qB.scalars.p, P.qC.scalars.p);
     const bool primary = P.ctx == 0;
     if (primary) ZK_CUDA(cudaEventRecord(k->mark[2], st));
-    // tails (bucket reduction, affine conversion) of A and C overlap the next accumulation; an error
-    // between run() and join() drains the device and drops the queued tails (PipelineScope)
+    // the three MSMs are queued first; an error before their tails have been enqueued drains the
+    // device and drops the queue (PipelineScope)
     PipelineScope<G1Traits> scope1(P.qC.table, P.ctx, nullptr, 2);
     PipelineScope<G2Traits> scope2(P.qB.table, P.ctx, nullptr, 1);
     XYZZ<Fp>* rA = np > 1 ? k->g1.p + p : P.r1.p;
     XYZZ<Fp>* rC = np > 1 ? k->g1.p + np + p : P.r1.p + 1;
     XYZZ<Fp2>* rB = np > 1 ? k->g2.p + p : P.r2.p;
     uint8_t* o = np > 1 ? nullptr : k->d_out.p;       // one part: wire bytes straight from the tail
-    P.qC.table.run(P.sA.p, 3 + L.ti_cnt, rA, o, st);                                                       // A
-    if (primary) ZK_CUDA(cudaEventRecord(k->mark[3], st));
-    P.qC.table.run(P.qC.scalars.p, P.qC.table.n, rC, o ? o + ZK_G1_OUT + ZK_G2_OUT : nullptr, st);         // C
-    if (primary) ZK_CUDA(cudaEventRecord(k->mark[4], st));
+    P.qC.table.run(P.sA.p, 3 + L.ti_cnt, rA, o, st);                                                       // A  } queued: one sort and
+    P.qC.table.run(P.qC.scalars.p, P.qC.table.n, rC, o ? o + ZK_G1_OUT + ZK_G2_OUT : nullptr, st);         // C  } one accumulation
     P.qB.table.run(P.qB.scalars.p, P.qB.table.n, rB, o ? o + ZK_G1_OUT : nullptr, st);                     // B
+    // the throughput-bound halves back to back on this stream, then the two latency-bound tails side
+    // by side (G2 on the auxiliary stream)
+    P.qC.table.sort_accumulate(st, primary ? k->mark[3] : nullptr);
+    if (primary) ZK_CUDA(cudaEventRecord(k->mark[4], st));
+    P.qB.table.sort_accumulate(st);
     if (primary) ZK_CUDA(cudaEventRecord(k->mark[5], st));
-    // all three accumulations are enqueued; the G2 tail runs on the auxiliary stream next to the G1 tail
     cudaStream_t aux = fork_aux(st);
-    P.qB.table.join(aux);
-    P.qC.table.join(st);
+    P.qB.table.tail(aux);
+    P.qC.table.tail(st);
     join_aux(st);
     if (primary) ZK_CUDA(cudaEventRecord(k->mark[6], st));
     if (np > 1) ZK_CUDA(cudaEventRecord(P.done, st));
@@ -348,9 +350,10 @@ int zk_groth16_last_device_ms(uint64_t pk_handle, float* ms) {
 }
 
 // Stage split of the last zk_groth16_prove* on this key, in ms (CUDA events on the primary device's
-// stream): [0] witness upload, [1] QAP evaluation + quotient h, [2] MSM scalars, [3] A, [4] C and
-// [5] B sorted + accumulated (the primary device's part), [6] batched tails of the three MSMs,
-// [7] wait for the other devices + combine + download.
+// stream): [0] witness upload, [1] QAP evaluation + quotient h, [2] MSM scalars, [3] counting sort of
+// A and C (one list), [4] their accumulation (one launch), [5] B sorted + accumulated (the primary
+// device's part), [6] tails of the G1 and G2 MSMs side by side, [7] wait for the other devices +
+// combine + download.
 int zk_groth16_last_stage_ms(uint64_t pk_handle, float out[8]) {
   ZK_API_BEGIN
   using namespace zk;
@@ -543,9 +546,13 @@ int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* s
   auto run2 = [&](int slot, uint8_t* out) { k->q2.table.run(at2(slot), k->cnt2[slot], nullptr, out, st, k->first2[slot]); };
   run1(0, o_vv); run1(1, o_yy); run1(5, o_h); run1(2, o_vav); run1(3, o_yay); run1(4, o_bvwy);
   run2(0, o_ww); run2(1, o_waw);
+  // the throughput-bound halves back to back on this stream (one sort and one accumulation per
+  // group), then the two latency-bound tails side by side
+  k->q1.table.sort_accumulate(st);
+  k->q2.table.sort_accumulate(st);
   cudaStream_t aux = fork_aux(st);
-  k->q2.table.join(aux);  // one batched tail for the two G2 elements, next to ...
-  k->q1.table.join(st);   // ... the one for the six G1 elements
+  k->q2.table.tail(aux);  // one batched tail for the two G2 elements, next to ...
+  k->q1.table.tail(st);   // ... the one for the six G1 elements
   join_aux(st);
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_PINOCCHIO_PROOF_OUT, cudaMemcpyDeviceToHost, st));
