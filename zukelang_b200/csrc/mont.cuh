@@ -13,6 +13,12 @@
 // likewise for odd j one limb higher, so each half is a single uninterrupted
 // mad.lo.cc / madc.hi.cc carry chain (IMAD pipe) with no carry fix-ups between
 // rows.  4N+1 IMADs per row, N rows.
+//
+// Provenance: the even/odd CIOS split and the row-helper vocabulary (mul_n, cmad_n,
+// madc_n_rshift, mad_row, final_sub) follow the scheme publicly documented for GPU Montgomery
+// arithmetic in the sppark / yrrid `mont_t` family (Apache-2.0); nothing is copied from those
+// sources — the code below was written against the PTX ISA.  mul2 (two interleaved products),
+// sqr_row (dedicated square) and the constexpr-immediate parameter classes are this project's own.
 #pragma once
 #include "ptx.cuh"
 
