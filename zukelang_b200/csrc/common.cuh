@@ -134,6 +134,26 @@ __device__ __forceinline__ void store_vec(T* p, const T& v) {
   for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
 }
 
+// Streaming variants (ld/st.global.cs: evict-first): for data that is written once and read once per
+// join — sorted entries, bucket sums, partial pieces — so that it does not push the randomly
+// gathered base table out of L2.
+template <class T>
+__device__ __forceinline__ T load_vec_stream(const T* p) {
+  T r;
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+  uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldcs(s + i);
+  return r;
+}
+template <class T>
+__device__ __forceinline__ void store_vec_stream(T* p, const T& v) {
+  uint4* d = reinterpret_cast<uint4*>(p);
+  const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) __stcs(d + i, s[i]);
+}
+
 // ---- byte formats (zcash / blst, see include/zkb200.h) -----------------------
 // 48 big-endian bytes -> raw (non-Montgomery) limbs; returns false if >= p
 __device__ __forceinline__ bool fp_from_be(const uint8_t* b, Fp& out, uint8_t mask0 = 0xff) {

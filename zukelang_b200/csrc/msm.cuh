@@ -132,7 +132,7 @@ k_digits(QueueSlots q, const uint8_t* __restrict__ skip, uint32_t stride, MsmCon
       uint32_t pos = atomicAdd(&counts_or_cursor[bucket], 1u);
       uint32_t idx = (cfg.nwb == 1) ? (uint32_t)w * stride + first + i : first + i;
       ZK_DCHECK(pos < entries_cap && first + i < stride);
-      entries[pos] = idx | (neg << 31);
+      __stcs(&entries[pos], idx | (neg << 31));
     } else {
       atomicAdd(&counts_or_cursor[bucket], 1u);
     }
@@ -258,11 +258,11 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
     for (int j = 0; j < VEC; j++) cp_async16(&acc_stage[(buf * VEC + j) * ACC_THREADS + threadIdx.x], src + j);
     cp_async_commit();
   };
-  uint32_t e = entries[e0];
+  uint32_t e = __ldcs(&entries[e0]);
   uint32_t e_next = 0;
   if (STAGED) {
     issue(0, e);
-    if (e0 + 1 < e1) e_next = entries[e0 + 1];
+    if (e0 + 1 < e1) e_next = __ldcs(&entries[e0 + 1]);
   }
   // bucket of entry e0: largest b with offsets[b] <= e0
   uint32_t lo = 0, hi = nbuckets;
@@ -284,10 +284,10 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
       const bool more = k + 1 < e1;
       if (more) issue(buf ^ 1, e_next);
       uint32_t e_next2 = 0;
-      if (k + 2 < e1) e_next2 = entries[k + 2];
+      if (k + 2 < e1) e_next2 = __ldcs(&entries[k + 2]);
       if (k >= b_end) {  // bucket b is finished: it started at seg_start
         const bool complete = seg_start == offsets[b];
-        store_vec(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);   // incomplete => started before e0
+        store_vec_stream(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);   // incomplete => started before e0
         acc = XYZZ<F>::inf();
         do { b++; ZK_DCHECK(b < nbuckets); b_end = offsets[b + 1]; } while (b_end <= k);
         seg_start = k;
@@ -303,12 +303,12 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
     } else {
       if (k >= b_end) {
         const bool complete = seg_start == offsets[b];
-        store_vec(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);
+        store_vec_stream(complete ? &bucket_sums[b] : &partial[2 * (size_t)t], acc);
         acc = XYZZ<F>::inf();
         do { b++; ZK_DCHECK(b < nbuckets); b_end = offsets[b + 1]; } while (b_end <= k);
         seg_start = k;
       }
-      e = entries[k];
+      e = __ldcs(&entries[k]);
       ZK_DCHECK((e & 0x7fffffffu) < npoints);
       cur = load_vec(&bases[e & 0x7fffffffu]);
       if (e >> 31) cur.y = cur.y.neg();
@@ -319,8 +319,8 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ e
   ZK_DCHECK(b < nbuckets && 2 * (size_t)t + 1 < 2 * (size_t)T);
   const bool starts_here = seg_start == offsets[b];
   const bool ends_here = e1 == b_end;
-  if (starts_here && ends_here) store_vec(&bucket_sums[b], acc);
-  else store_vec(&partial[2 * (size_t)t + (e0 >= offsets[b] ? 0 : 1)], acc);
+  if (starts_here && ends_here) store_vec_stream(&bucket_sums[b], acc);
+  else store_vec_stream(&partial[2 * (size_t)t + (e0 >= offsets[b] ? 0 : 1)], acc);
   // the bucket this slice stops inside of (it continues in slice t + 1), for k_fix_partials
   open_bucket[t] = ends_here ? 0xffffffffu : b;
 }
@@ -436,7 +436,7 @@ k_reduce_chunks(const XYZZ<F>* __restrict__ bucket_sums_all, const uint32_t* __r
   for (int j = cfg.L - 1; j >= 0; j--) {
     const uint32_t lo = offsets[first + j];
     if (lo != hi) {                       // an empty bucket was never written: it is the identity
-      XYZZ<F> p = load_vec_rw(&bucket_sums[first + j]);
+      XYZZ<F> p = load_vec_stream(&bucket_sums[first + j]);
       run.add(p);
     }
     hi = lo;
