@@ -56,6 +56,13 @@ def _run_config(zk, circ, wit, seed, shards=0, verify=True):
     r, s = rng.randrange(R), rng.randrange(R)
     proof = P.prove_with(r, s, dom, pk, sol)
     assert proof.to_compressed_bytes() == _oracle_proof_bytes(td, r, s, circ, sol)
+    # the stage split of that proof adds up to its device time (zk_groth16_last_stage_ms)
+    from zukelang_b200 import _lib
+    ms, stages = ctypes.c_float(), (ctypes.c_float * 8)()
+    hk = P._key_handle(pk, dom.circuit)
+    _lib.check(zk.zk_groth16_last_device_ms(hk, ctypes.byref(ms)))
+    _lib.check(zk.zk_groth16_last_stage_ms(hk, stages))
+    assert all(x >= 0 for x in stages) and abs(sum(stages) - ms.value) <= 0.02 * ms.value + 0.05
     if verify:
         pub = {k: sol[k] for k in vk.ltgm_io}
         assert P.verify(pub, vk, proof)

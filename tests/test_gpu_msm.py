@@ -150,6 +150,22 @@ def test_table_msm_batch_and_pipelined_dev(zk):
         st.synchronize()
         assert [bytes(d_out[i].cpu().numpy()) for i in range(count)] == expect
         _lib.check(zk.zk_table_pipeline(h.value, 0))
+        # stage events: every join is recorded with the MSMs it held (zk_table_profile_totals)
+        _lib.check(zk.zk_table_profile(h.value, 1, None))
+        _lib.check(zk.zk_table_pipeline(h.value, 4))
+        d_out.zero_()
+        with torch.cuda.stream(st):
+            for i in range(6):                      # a full queue of 4 is joined by the 5th call, the rest by the join
+                _lib.check(zk.zk_g1_table_msm_dev(h.value, d_sc[i].data_ptr(), n, d_out[i].data_ptr(), st.cuda_stream))
+            _lib.check(zk.zk_table_join(h.value, st.cuda_stream))
+        st.synchronize()
+        assert [bytes(d_out[i].cpu().numpy()) for i in range(6)] == expect[:6]
+        totals, counts, last = (ctypes.c_float * 4)(), (ctypes.c_uint64 * 2)(), (ctypes.c_float * 4)()
+        _lib.check(zk.zk_table_profile_totals(h.value, totals, counts))
+        _lib.check(zk.zk_table_profile(h.value, 0, last))
+        assert (counts[0], counts[1]) == (6, 2)
+        assert all(t > 0 for t in totals) and all(0 < last[i] <= totals[i] for i in range(4))
+        _lib.check(zk.zk_table_pipeline(h.value, 0))
     finally:
         _lib.check(zk.zk_table_free(h.value))
 

@@ -649,7 +649,7 @@ struct BaseTable {
   // queued, tail() the batched reduction of what sort_accumulate() left pending (any stream that is
   // ordered after it).
   void sort_accumulate(cudaStream_t st, cudaEvent_t after_scatter = nullptr);
-  void tail(cudaStream_t st);
+  void tail(cudaStream_t st, int share = 1);   // share = tails of this many tables run side by side
   // pipelined = queue up to `depth` MSMs per join (allocates the buffers for that many on first use);
   // depth 0 = the default depth (ZKB200_QUEUE, 32), at most MSM_QUEUE
   void set_pipelined(bool on, int depth = 0);

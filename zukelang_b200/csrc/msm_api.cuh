@@ -224,11 +224,12 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
   }
   // Size of the first group: large enough that its computation (s per MSM, plus one tail) covers the
   // upload of everything after it (u per MSM), small enough that little upload time is exposed
-  // before the first kernel:  (count - g) u <= g s + tail.  u from 40 GB/s of pinned-host bandwidth,
-  // s from 0.38 ns per bucket addition, tail ~ 1.2 ms.
+  // before the first kernel:  (count - g) u <= g s + tail.  u from 25 GB/s of pinned-host bandwidth
+  // (what one of 8 processes uploading at once can count on; a lone process sees ~50), s from
+  // 0.38 ns per bucket addition, tail ~ 1.2 ms.
   size_t first_group = 1;
   {
-    const double u = (double)widest * 32 / 40e9, sdur = (double)widest * h->parts[0]->table.cfg.W * 0.38e-9, tail = 1.2e-3;
+    const double u = (double)widest * 32 / 25e9, sdur = (double)widest * h->parts[0]->table.cfg.W * 0.38e-9, tail = 1.2e-3;
     const double g = ((double)count * u - tail) / (sdur + u);
     if (g > 1) first_group = (size_t)g + 1;
     first_group = std::min<size_t>(first_group, (size_t)depth);

@@ -247,7 +247,7 @@ void BaseTable<T>::sort_accumulate(cudaStream_t st, cudaEvent_t after_scatter) {
 }
 
 template <class T>
-void BaseTable<T>::tail(cudaStream_t st) {
+void BaseTable<T>::tail(cudaStream_t st, int share) {
   if (pending == 0) return;
   const uint32_t nb = cfg.nbuckets();
   const int Q = pending;
@@ -262,12 +262,20 @@ void BaseTable<T>::tail(cudaStream_t st) {
     const int ht = sizeof(XYZZ<F>) > 192 ? 128 : 256;   // 48 KB of shared memory either way
     k_fix_heavy<F><<<sm_count(), ht, ht * sizeof(XYZZ<F>), st>>>(offsets.p, bucket_sums.p, partial.p, nbq, acc_threads, heavy.p);
   }
-  // ... bucket reduction.  Chunk width of the running sum: narrow (shallow dependency chain) for a
-  // single MSM, wider (fewer per-chunk scalar multiplications: 3.3 additions per bucket at L = 16 and
-  // 2.7 at L = 32, against 7.3 at L = 4) once the latency is shared by a batch — a batch of 8 or more
-  // keeps the machine busy with half as many threads, and then the work is what counts
+  // ... bucket reduction.  Chunk width L of the running sum: a chunk costs 2 L - 1 additions plus a
+  // ~22-operation scalar multiplication, all dependent, so narrow chunks mean a short chain but
+  // 7.3 additions per bucket (L = 4) against 3.3 (L = 16) or 2.7 (L = 32).  A lone warp already
+  // keeps its scheduler's multiplier slot busy, so the kernel is latency-bound up to one warp per
+  // scheduler and throughput-bound beyond: take the narrowest L that keeps the chunk threads of all
+  // queued MSMs within that (halved when another table's tail runs beside this one).
   MsmConfig rc = cfg;
-  if (Q >= 3 && env_int("ZKB200_REDUCE_CHUNK", 0) <= 0) { rc.L = Q >= 8 ? 32 : 16; while ((uint32_t)rc.L > rc.B) rc.L >>= 1; }
+  if (env_int("ZKB200_REDUCE_CHUNK", 0) <= 0) {
+    const uint64_t target = (uint64_t)sm_count() * 4 * 32 / (uint64_t)std::max(1, share);
+    int L = 4;
+    while (L < 32 && (uint64_t)Q * nb / L > target) L <<= 1;
+    rc.L = L;
+    while ((uint32_t)rc.L > rc.B) rc.L >>= 1;
+  }
   const uint32_t cpw = rc.B / rc.L;
   k_reduce_chunks<F><<<dim3(cdiv((size_t)cpw * cfg.nwb, TAIL_THREADS), 1, Q), TAIL_THREADS, 0, st>>>(bucket_sums.p, offsets.p, rc,
                                                                                                      chunk_out.p);

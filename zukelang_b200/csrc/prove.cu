@@ -231,10 +231,19 @@ static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* 
     if (primary) ZK_CUDA(cudaEventRecord(k->mark[4], st));
     P.qB.table.sort_accumulate(st);
     if (primary) ZK_CUDA(cudaEventRecord(k->mark[5], st));
-    cudaStream_t aux = fork_aux(st);
-    P.qB.table.tail(aux);
-    P.qC.table.tail(st);
-    join_aux(st);
+    static const int tail_mode = env_int("ZKB200_TAIL_MODE", 0);   // experiment knob: 1 = both tails on one stream, 2 = G2 only, 3 = G1 only
+    if (tail_mode == 0) {
+      cudaStream_t aux = fork_aux(st);
+      P.qB.table.tail(aux, 2);
+      P.qC.table.tail(st, 2);
+      join_aux(st);
+    } else {
+      if (tail_mode != 3) P.qB.table.tail(st);
+      if (primary && tail_mode == 1) ZK_CUDA(cudaEventRecord(k->mark[5], st));   // [6] then times the G1 tail alone
+      if (tail_mode != 2) P.qC.table.tail(st);
+      P.qB.table.abort_queue();
+      P.qC.table.abort_queue();
+    }
     if (primary) ZK_CUDA(cudaEventRecord(k->mark[6], st));
     if (np > 1) ZK_CUDA(cudaEventRecord(P.done, st));
   }
@@ -551,8 +560,8 @@ int zk_pinocchio_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* s
   k->q1.table.sort_accumulate(st);
   k->q2.table.sort_accumulate(st);
   cudaStream_t aux = fork_aux(st);
-  k->q2.table.tail(aux);  // one batched tail for the two G2 elements, next to ...
-  k->q1.table.tail(st);   // ... the one for the six G1 elements
+  k->q2.table.tail(aux, 2);  // one batched tail for the two G2 elements, next to ...
+  k->q1.table.tail(st, 2);   // ... the one for the six G1 elements
   join_aux(st);
   int fl[2];
   ZK_CUDA(cudaMemcpyAsync(proof_out, k->d_out.p, ZK_PINOCCHIO_PROOF_OUT, cudaMemcpyDeviceToHost, st));
