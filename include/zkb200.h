@@ -242,10 +242,11 @@ typedef struct {
 /* Device time (ms, CUDA events on the primary device's stream: first upload to last download) of
  * the last zk_groth16_prove* call on this key; for bench.py. */
 int zk_groth16_last_device_ms(uint64_t pk, float *ms);
-/* Stage split of that time, in ms: [0] witness upload, [1] QAP evaluation + quotient h(x),
- * [2] MSM scalars, [3] counting sort of A and C (one entry list), [4] their accumulation (one
- * launch), [5] B sorted and accumulated (the primary device's part), [6] tails of the G1 and G2
- * MSMs side by side, [7] wait for the other devices + combine + download. */
+/* Stage split of that time, in ms (primary device): [0] witness upload, [1] QAP evaluation
+ * (V | W | Y), [2] B: scalars, counting sort, accumulation, [3] quotient h(x) — B's tail runs beside
+ * it on a second stream —, [4] A and C: scalars and counting sort (one entry list), [5] their
+ * accumulation (one launch), [6] the G1 tail and what is left of the G2 tail, [7] wait for the
+ * other devices + combine + download. */
 int zk_groth16_last_stage_ms(uint64_t pk, float out[8]);
 
 int zk_pinocchio_pk_load(const zk_pinocchio_pkey *pk, int shard_index, int shard_count, uint64_t *handle);

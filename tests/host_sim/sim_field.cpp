@@ -23,6 +23,9 @@ static void binop(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     case 7: r = x.dbl(); break;
     case 8: r = x.inverse_fermat(); break;
     case 9: r = x.sqr(); break;
+    case 10: { F r2; F::mul2(x, y, y, y, r, r2); r = r + r2; break; }           // x y + y y, interleaved rows
+    case 11: { F r2; F::mul2_rolled(x, y, y, y, r, r2); r = r + r2; break; }    // same, rolled row loop
+    case 12: { F r2; F::mul2_rolled(y, y, x, y, r2, r); r = r + r2; break; }    // operands swapped between the two products
     default: r = F::zero();
   }
   memcpy(out, r.v, sizeof(r.v));

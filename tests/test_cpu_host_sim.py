@@ -52,6 +52,10 @@ def test_montgomery_limb_algorithms(sim, which, mod, n):
         assert _field(fn, n, 4, a) == a * Rm % mod
         assert _field(fn, n, 5, a) == a * Ri % mod
         assert _field(fn, n, 9, a) == a * a * Ri % mod               # dedicated squaring
+        both = (a * b + b * b) * Ri % mod
+        assert _field(fn, n, 10, a, b) == both                       # two products, rows interleaved
+        assert _field(fn, n, 11, a, b) == both                       # ... with the row loop rolled
+        assert _field(fn, n, 12, a, b) == both
     for a in vals[:40]:
         exp = (pow(a, -1, mod) * Rm % mod) if a else 0
         assert _field(fn, n, 6, a * Rm % mod) == exp                 # binary extended Euclid

@@ -198,7 +198,7 @@ def run(zk, logn, iters, circuit="mulchain", dist=None, quiet=False):
            "processes": world, "devices_per_process": ndev,
            "prove_ms": med(wall), "prove_ms_best": min(wall), "prove_ms_all": wall,
            "device_ms": med(dev), "device_ms_all": dev, "proofs_per_s": 1e3 / med(wall), "exact_ok": bool(ok),
-           "stages_ms": dict(zip(("upload", "qap_eval_quotient", "msm_scalars", "AC_g1_sort", "AC_g1_accumulate", "B_g2_sort_accumulate", "tails", "combine_download"),
+           "stages_ms": dict(zip(("upload", "qap_values", "B_g2_scalars_sort_accumulate", "quotient_h", "AC_g1_scalars_sort", "AC_g1_accumulate", "tails", "combine_download"),
                                  stages[len(stages) // 2])),
            "stages_note": "CUDA events on this process' primary stream, one timed proof (rank 0's when sharded)",
            "setup_s": setup_s, "witness_memory": "pinned host", "h2d_bytes_per_proof": 32 * len(circ.variables) + 64, "d2h_bytes_per_proof": 576,

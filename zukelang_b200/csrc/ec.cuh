@@ -25,7 +25,20 @@ static __device__ __noinline__ FpPair fp_mul2_outofline(Fp a, Fp b, Fp c, Fp d) 
   Fp::mul2(a, b, c, d, r.lo, r.hi);
   return r;
 }
+// The same pair of products with the row loop rolled (Mont::mul2_rolled): ~8 KB of code.  What the
+// out-of-line point formulas below call — the latency-bound kernels spend their time waiting for
+// instructions, not for the multiplier (see mont.cuh).
+static __device__ __noinline__ FpPair fp_mul2_compact(Fp a, Fp b, Fp c, Fp d) {
+  FpPair r;
+  Fp::mul2_rolled(a, b, c, d, r.lo, r.hi);
+  return r;
+}
 #else
+static inline FpPair fp_mul2_compact(Fp a, Fp b, Fp c, Fp d) {
+  FpPair r;
+  Fp::mul2_rolled(a, b, c, d, r.lo, r.hi);
+  return r;
+}
 static inline Fp fp_mul_outofline(Fp a, Fp b) { return a * b; }
 static inline FpPair fp_mul2_outofline(Fp a, Fp b, Fp c, Fp d) {
   FpPair r;
@@ -106,6 +119,47 @@ struct FpCall {
 };
 
 // -------------------------------------------------------------------------
+// Products of the OUT-OF-LINE point formulas (add, dbl, to_affine: bucket reduction, fix-ups,
+// window combine, ladders).  Every product goes through the one compact routine above, in
+// independent pairs, so that a whole latency-bound kernel is a few tens of KB of code: r1 = a b,
+// r2 = c d; lat_sqr2 = two independent squares.
+// -------------------------------------------------------------------------
+ZK_HD void lat_mul2(const Fp& a, const Fp& b, const Fp& c, const Fp& d, Fp& r1, Fp& r2) {
+  FpPair p = fp_mul2_compact(a, b, c, d);
+  r1 = p.lo;
+  r2 = p.hi;
+}
+ZK_HD void lat_mul2(const FpCall& a, const FpCall& b, const FpCall& c, const FpCall& d, FpCall& r1, FpCall& r2) {
+  FpPair p = fp_mul2_compact(a.f, b.f, c.f, d.f);
+  r1.f = p.lo;
+  r2.f = p.hi;
+}
+// (out of line themselves: the ten Fp additions around the three calls are 6 KB of code, and a G2
+// addition makes seven of these)
+static ZK_NI void lat_mul2(const Fp2& a, const Fp2& b, const Fp2& c, const Fp2& d, Fp2& r1, Fp2& r2) {
+  FpPair p0 = fp_mul2_compact(a.c0, b.c0, c.c0, d.c0);
+  FpPair p1 = fp_mul2_compact(a.c1, b.c1, c.c1, d.c1);
+  FpPair pm = fp_mul2_compact(a.c0 + a.c1, b.c0 + b.c1, c.c0 + c.c1, d.c0 + d.c1);
+  r1 = Fp2{p0.lo - p1.lo, pm.lo - p0.lo - p1.lo};
+  r2 = Fp2{p0.hi - p1.hi, pm.hi - p0.hi - p1.hi};
+}
+ZK_HD void lat_sqr2(const Fp& a, const Fp& b, Fp& ra, Fp& rb) { lat_mul2(a, a, b, b, ra, rb); }
+ZK_HD void lat_sqr2(const FpCall& a, const FpCall& b, FpCall& ra, FpCall& rb) { lat_mul2(a, a, b, b, ra, rb); }
+static ZK_NI void lat_sqr2(const Fp2& a, const Fp2& b, Fp2& ra, Fp2& rb) {
+  // (c0 + c1 u)^2 = (c0 + c1)(c0 - c1) + 2 c0 c1 u
+  FpPair x = fp_mul2_compact(a.c0 + a.c1, a.c0 - a.c1, a.c0, a.c1);
+  FpPair y = fp_mul2_compact(b.c0 + b.c1, b.c0 - b.c1, b.c0, b.c1);
+  ra = Fp2{x.lo, x.hi.dbl()};
+  rb = Fp2{y.lo, y.hi.dbl()};
+}
+template <class F>
+ZK_HD F lat_mul(const F& a, const F& b) {
+  F r, unused;
+  lat_mul2(a, b, a, b, r, unused);
+  return r;
+}
+
+// -------------------------------------------------------------------------
 // points
 // -------------------------------------------------------------------------
 template <class F>
@@ -129,22 +183,24 @@ struct XYZZ {
   ZK_HD XYZZ neg() const { return XYZZ{X, Y.neg(), ZZ, ZZZ}; }
 
   // The out-of-line formulas below (latency-bound callers: bucket reduction, fix-ups, window
-  // combine, fixed-base ladders) issue their independent products as interleaved pairs (F::mul2):
-  // a lone warp then overlaps two carry chains instead of waiting on one.
+  // combine, fixed-base ladders) issue their independent products as interleaved pairs through ONE
+  // compact out-of-line routine (lat_mul2): a lone warp overlaps two carry chains instead of waiting
+  // on one, and the kernels stay small enough for the instruction caches.
 
   // 2 * (affine p)   — mdbl-2008-s-1
   static ZK_NI XYZZ dbl_affine(const Affine<F>& p) {
     if (p.is_inf() || p.y.is_zero()) return inf();
     F U = p.y.dbl();
-    F V = U.sqr();
-    F xx = p.x.sqr();
+    F V, xx;
+    lat_sqr2(U, p.x, V, xx);
     F W, S;
-    F::mul2(U, V, p.x, V, W, S);
+    lat_mul2(U, V, p.x, V, W, S);
     F M = xx.dbl() + xx;
     XYZZ r;
-    r.X = M.sqr() - S.dbl();
-    F t1, t2;
-    F::mul2(M, S - r.X, W, p.y, t1, t2);
+    F MM, t2;
+    lat_mul2(M, M, W, p.y, MM, t2);
+    r.X = MM - S.dbl();
+    F t1 = lat_mul(M, S - r.X);
     r.Y = t1 - t2;
     r.ZZ = V;
     r.ZZZ = W;
@@ -155,17 +211,19 @@ struct XYZZ {
   ZK_NI XYZZ dbl() const {
     if (is_inf() || Y.is_zero()) return inf();
     F U = Y.dbl();
-    F V = U.sqr();
-    F xx = X.sqr();
+    F V, xx;
+    lat_sqr2(U, X, V, xx);
     F W, S;
-    F::mul2(U, V, X, V, W, S);
+    lat_mul2(U, V, X, V, W, S);
     F M = xx.dbl() + xx;
     XYZZ r;
-    r.X = M.sqr() - S.dbl();
-    F t1, t2;
-    F::mul2(M, S - r.X, W, Y, t1, t2);
+    F MM, t2;
+    lat_mul2(M, M, W, Y, MM, t2);
+    r.X = MM - S.dbl();
+    F t1;
+    lat_mul2(M, S - r.X, V, ZZ, t1, r.ZZ);
     r.Y = t1 - t2;
-    F::mul2(V, ZZ, W, ZZZ, r.ZZ, r.ZZZ);
+    r.ZZZ = lat_mul(W, ZZZ);
     return r;
   }
 
@@ -223,13 +281,13 @@ struct XYZZ {
     ZZZ = ZZZ * PPP;
   }
 
-  // this += q   — add-2008-s, products in interleaved pairs (7 pair steps for 12M + 2S)
+  // this += q   — add-2008-s, products in independent pairs (7 pair steps for 12M + 2S)
   ZK_NI void add(const XYZZ& q) {
     if (q.is_inf()) return;
     if (is_inf()) { *this = q; return; }
     F U1, U2, S1, S2;
-    F::mul2(X, q.ZZ, q.X, ZZ, U1, U2);
-    F::mul2(Y, q.ZZZ, q.Y, ZZZ, S1, S2);
+    lat_mul2(X, q.ZZ, q.X, ZZ, U1, U2);
+    lat_mul2(Y, q.ZZZ, q.Y, ZZZ, S1, S2);
     F Pd = U2 - U1;
     F Rd = S2 - S1;
     if (Pd.is_zero()) {
@@ -237,15 +295,15 @@ struct XYZZ {
       else *this = inf();
       return;
     }
-    F PP = Pd.sqr();
-    F RR = Rd.sqr();
+    F PP, RR;
+    lat_sqr2(Pd, Rd, PP, RR);
     F PPP, Q;
-    F::mul2(Pd, PP, U1, PP, PPP, Q);
+    lat_mul2(Pd, PP, U1, PP, PPP, Q);
     F X3 = RR - PPP - Q.dbl();
     F t1, t2, z2, z3;
-    F::mul2(Rd, Q - X3, S1, PPP, t1, t2);
-    F::mul2(ZZ, q.ZZ, ZZZ, q.ZZZ, z2, z3);
-    F::mul2(z2, PP, z3, PPP, ZZ, ZZZ);
+    lat_mul2(Rd, Q - X3, S1, PPP, t1, t2);
+    lat_mul2(ZZ, q.ZZ, ZZZ, q.ZZZ, z2, z3);
+    lat_mul2(z2, PP, z3, PPP, ZZ, ZZZ);
     Y = t1 - t2;
     X = X3;
   }
@@ -255,9 +313,10 @@ struct XYZZ {
     if (is_inf()) return Affine<F>::inf();
     // 1/ZZZ * ZZ = 1/Z  ->  1/ZZ = (1/Z)^2
     F izzz = ZZZ.inverse();
-    F iz = izzz * ZZ;
-    F izz = iz.sqr();
-    return Affine<F>{X * izz, Y * izzz};
+    F iz, y;
+    lat_mul2(izzz, ZZ, Y, izzz, iz, y);
+    F izz = lat_mul(iz, iz);
+    return Affine<F>{lat_mul(X, izz), y};
   }
 };
 

@@ -540,6 +540,11 @@ void EvalDomain::load_matrix(int which, uint32_t m_, const uint32_t* row_ptr, co
 }
 
 void EvalDomain::eval(const uint32_t* d_sol_raw, cudaStream_t st) {
+  values(d_sol_raw, st);
+  quotient(st);
+}
+
+void EvalDomain::values(const uint32_t* d_sol_raw, cudaStream_t st) {
   const uint32_t D = plan.D;
   ZK_REQUIRE(mat[0].row_ptr.p && mat[1].row_ptr.p && mat[2].row_ptr.p, ZK_EARG, "prove_r1cs: matrices not loaded");
   ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
@@ -548,6 +553,11 @@ void EvalDomain::eval(const uint32_t* d_sol_raw, cudaStream_t st) {
   for (int q = 0; q < 3; q++) { P.row_ptr[q] = mat[q].row_ptr.p; P.col[q] = mat[q].col.p; P.val[q] = mat[q].val.p; }
   k_csr_matvec<<<dim3(cdiv(n, 128), 3), 128, 0, st>>>(P, sol_m.p, n, m, evals.p);
   k_eval_prepare<<<cdiv(D, 128), 128, 0, st>>>(evals.p, w.p, n, D, work.p, flag.p + 1);
+  ZK_CUDA(cudaGetLastError());
+}
+
+void EvalDomain::quotient(cudaStream_t st) {
+  const uint32_t D = plan.D;
   ntt_forward_batch(plan, work.p, 3, st);
   k_mul_by_ghat<<<cdiv(D, 256), 256, 0, st>>>(work.p, ghat.p, D);
   ntt_inverse_batch(plan, work.p, 3, st);
@@ -603,12 +613,17 @@ void QapDevice::load(const uint8_t* v, const uint8_t* w, const uint8_t* y, const
 }
 
 void QapDevice::eval(const uint32_t* d_sol_raw, cudaStream_t st) {
+  combine(d_sol_raw, st);
+  quotient_from_work(st);
+}
+
+void QapDevice::combine(const uint32_t* d_sol_raw, cudaStream_t st) {
   const uint32_t D = plan.D;
   ZK_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), st));
   fr_to_mont(d_sol_raw, sol_m.p, m, flag.p, st);
   k_qap_combine<<<dim3(cdiv(D, COMBINE_X), 3), dim3(COMBINE_X, COMBINE_K), 0, st>>>(vm.p, wm.p, ym.p, sol_m.p, m, n, D,
                                                                                      plan.coset.p, Vc.p, V.p);
-  quotient_from_work(st);
+  ZK_CUDA(cudaGetLastError());
 }
 
 void QapDevice::quotient_from_work(cudaStream_t st) {

@@ -48,6 +48,9 @@ struct QapDevice {
             cudaStream_t st);
   // d_sol_raw: m canonical scalars on the device.  Enqueues QAP.eval: fills Vc and H.
   void eval(const uint32_t* d_sol_raw, cudaStream_t st);
+  // its two halves: combine() fills Vc (the A / B scalars) and the coset-shifted work vectors,
+  // quotient_from_work() then computes H — a prover can start the B query in between
+  void combine(const uint32_t* d_sol_raw, cudaStream_t st);
   // V | W | Y given directly as 3 * n canonical scalars on the device
   void set_coeffs(const uint32_t* d_vwy_raw, cudaStream_t st);
   void quotient_from_work(cudaStream_t st);
@@ -82,6 +85,10 @@ struct EvalDomain {
                    cudaStream_t st);
   // d_sol_raw: m canonical scalars.  Fills evals and H; sets flag[1] if a gate is violated.
   void eval(const uint32_t* d_sol_raw, cudaStream_t st);
+  // its two halves: values() fills evals (V | W | Y on the domain: the A / B scalars) and checks the
+  // gates, quotient() extrapolates and fills H — a prover can start the B query in between
+  void values(const uint32_t* d_sol_raw, cudaStream_t st);
+  void quotient(cudaStream_t st);
 };
 struct EvalDomainHandle : HandleBase {
   EvalDomain d;

@@ -196,6 +196,42 @@ struct alignas(16) Mont {
     final_sub(r2, 0);
   }
 
+  // mul2 with the row loop ROLLED (two rows of each product per iteration): ~8 KB of code instead of
+  // ~22 KB, and a loop body that fits the 6 KB L0 instruction cache.  For the latency-bound callers
+  // (bucket reduction, fix-ups, fixed-base ladders, affine conversion): their fully inlined formulas
+  // were 200 KB per kernel, far beyond the 32 KB L1.5 instruction cache, and ncu shows them waiting
+  // for instructions (`no_instruction` 3.2 warps per issue) more than for operands.  The row operands
+  // b_i, d_i are taken from rotating register copies, so no index is dynamic.
+  static ZK_HD void mul2_rolled(const Mont& a, const Mont& b, const Mont& c, const Mont& d, Mont& r1, Mont& r2) {
+    uint32_t e1[N], o1[N], e2[N], o2[N], bb[N], dd[N];
+    ZK_UNROLL for (int j = 0; j < N; j++) { bb[j] = b.v[j]; dd[j] = d.v[j]; }
+    mul_n<N>(e1, a.v, bb[0]);
+    mul_n<N>(e2, c.v, dd[0]);
+    mul_n<N>(o1, a.v + 1, bb[0]);
+    mul_n<N>(o2, c.v + 1, dd[0]);
+    reduce_row(e1, o1);
+    reduce_row(e2, o2);
+    ZK_NOUNROLL for (int it = 0; it < (N - 1) / 2; it++) {   // rows (1, 2), (3, 4), ...
+      mad_row(o1, e1, a.v, bb[1]);
+      mad_row(o2, e2, c.v, dd[1]);
+      mad_row(e1, o1, a.v, bb[2]);
+      mad_row(e2, o2, c.v, dd[2]);
+      ZK_UNROLL for (int j = 1; j + 2 < N; j++) { bb[j] = bb[j + 2]; dd[j] = dd[j + 2]; }
+    }
+    if ((N - 1) & 1) {                                       // the last row when N is even
+      mad_row(o1, e1, a.v, bb[1]);
+      mad_row(o2, e2, c.v, dd[1]);
+    }
+    r1.v[0] = ptx::add_cc(e1[0], o1[1]);
+    ZK_UNROLL for (int i = 1; i < N - 1; i++) r1.v[i] = ptx::addc_cc(e1[i], o1[i + 1]);
+    r1.v[N - 1] = ptx::addc(e1[N - 1], 0);
+    r2.v[0] = ptx::add_cc(e2[0], o2[1]);
+    ZK_UNROLL for (int i = 1; i < N - 1; i++) r2.v[i] = ptx::addc_cc(e2[i], o2[i + 1]);
+    r2.v[N - 1] = ptx::addc(e2[N - 1], 0);
+    final_sub(r1, 0);
+    final_sub(r2, 0);
+  }
+
   // ---- Montgomery square ---------------------------------------------------------
   // a^2 = sum_i a_i * e^(i) * 2^(32 i) with e^(i) = (0, .., 0, a_i, 2 a_{i+1}, .., 2 a_{N-1}): row i of
   // the CIOS loop only multiplies the limbs j >= i, 78 partial products for N = 12 instead of 144

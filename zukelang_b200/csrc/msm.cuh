@@ -627,6 +627,7 @@ struct BaseTable {
   int pending = 0;           // MSMs sorted and accumulated whose tail has not been enqueued yet
   uint32_t pending_threads = 0;   // threads their accumulation ran with
   int queue_cap = 0;         // MSMs one join can take with the buffers currently allocated (1 unless pipelined)
+  int queue_limit = 1;       // MSMs the caller asked to queue at most (<= queue_cap): run() joins when it is reached
   QueueSlots slots{};
   TailOutputs<F> outs{};
   bool pipelined = false;    // false: every run() joins immediately (plain stream order)

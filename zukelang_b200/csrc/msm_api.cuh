@@ -209,7 +209,7 @@ int api_table_msm_batch(uint64_t handle, const uint8_t* const* scalars, size_t n
     CtxScope scope(P.ctx);
     if (!P.batch.copy) P.batch.ensure(0, 0);                     // the copy stream, for the scope below
     scopes.push_back(std::make_unique<PipelineScope<T>>(P.table, P.ctx, P.batch.copy));
-    depth = std::min(depth, P.table.queue_cap);
+    depth = std::min(depth, std::min(P.table.queue_cap, P.table.queue_limit));
   }
   depth = (int)std::min<size_t>((size_t)depth, count);
   size_t widest = 0;

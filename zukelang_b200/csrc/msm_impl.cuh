@@ -108,6 +108,7 @@ void BaseTable<T>::build_tables(cudaStream_t st) {
   open_bucket.alloc((size_t)acc_blocks * ACC_THREADS);
   queued = 0;
   queue_cap = 0;
+  queue_limit = 1;
   pipelined = false;
   ensure_queue(1);
   if (env_int("ZKB200_PIPELINE", 0) != 0) set_pipelined(true);
@@ -121,7 +122,7 @@ void BaseTable<T>::run(const uint32_t* d_scalars, uint32_t count, XYZZ<F>* d_res
   ZK_REQUIRE(count > 0 && (uint64_t)first + count <= n, ZK_EARG, "scalar range exceeds the base table");
   ZK_REQUIRE(d_scalars, ZK_EARG, "null scalar vector");
   if (pending) tail(st);              // a sort_accumulate() whose tail was never asked for
-  if (queued >= queue_cap) join(st);
+  if (queued >= std::min(queue_cap, queue_limit)) join(st);
   const int slot = queued;
   slots.scalars[slot] = d_scalars;
   slots.err[slot] = d_err;
@@ -192,7 +193,8 @@ template <class T>
 void BaseTable<T>::set_pipelined(bool on, int depth) {
   if (on) {
     if (depth <= 0) depth = env_int("ZKB200_QUEUE", MSM_QUEUE);
-    if (queued == 0) ensure_queue(depth);   // cannot grow under queued MSMs: the current depth stays
+    if (queued == 0) ensure_queue(depth);   // cannot grow under queued MSMs: the current capacity stays
+    queue_limit = std::max(std::max(1, queued), std::min(depth, queue_cap));
   }
   pipelined = on;
 }

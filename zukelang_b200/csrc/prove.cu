@@ -21,6 +21,7 @@
 // shards' partials (one tiny gather) to obtain the proof.
 #include <string.h>
 #include <algorithm>
+#include <functional>
 #include "fr_poly.cuh"
 #include "msm.cuh"
 #include "runtime.cuh"
@@ -84,42 +85,48 @@ struct Groth16Key : HandleBase {
   DevBuf<XYZZ<Fp>> g1;      // [A, C][part]
   DevBuf<XYZZ<Fp2>> g2;     // [part]
   DevBuf<uint8_t> d_out;
-  cudaEvent_t ready = nullptr;
+  cudaEvent_t ready = nullptr, ready_h = nullptr;   // primary stream: V | W ready / h ready (the other devices wait on them)
   cudaEvent_t t_begin = nullptr, t_end = nullptr;   // device time of the last prove (zk_groth16_last_device_ms)
+  bool early_b_last = true;                         // order of the last prove: B before the quotient (large circuits) or after A and C
   // stage marks of the last prove on the primary device's stream (zk_groth16_last_stage_ms):
-  // 0 witness uploaded, 1 V | W | Y and h ready, 2 MSM scalars written, 3 A and C sorted, 4 A and C
-  // accumulated, 5 B sorted and accumulated (primary device's part), 6 tails joined (primary part)
+  // 0 witness uploaded, 1 V | W | Y ready, 2 B sorted and accumulated, 3 h ready, 4 A and C sorted,
+  // 5 A and C accumulated, 6 tails joined (primary device's part throughout)
   static constexpr int NMARK = 7;
   cudaEvent_t mark[NMARK] = {};
   Groth16Key() { kind = 4; }
   ~Groth16Key() {
     if (ready) cudaEventDestroy(ready);
+    if (ready_h) cudaEventDestroy(ready_h);
     if (t_begin) cudaEventDestroy(t_begin);
     if (t_end) cudaEventDestroy(t_end);
     for (cudaEvent_t e : mark) if (e) cudaEventDestroy(e);
   }
 };
 
+// which & 1: the scalars of B (needs V | W only); which & 2: those of A and C (needs h as well)
 static __global__ void __launch_bounds__(128)
-k_groth16_scalars(G16Layout L, const Fr* __restrict__ vwy, const Fr* __restrict__ H,
+k_groth16_scalars(G16Layout L, int which, const Fr* __restrict__ vwy, const Fr* __restrict__ H,
                   const uint32_t* __restrict__ sol_raw, const uint32_t* __restrict__ mid_index,
                   const uint32_t* __restrict__ rs_raw, uint32_t* __restrict__ sA, uint32_t* __restrict__ sB,
                   uint32_t* __restrict__ sC) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const Fr r_raw = get_raw(rs_raw, 0), s_raw = get_raw(rs_raw, 1);
+  const bool own = L.singles != 0;
+  const Fr zero = Fr::zero();
+  if (which & 1) {
+    if (t == 0) { put_raw(sB, 0, own ? raw_one() : zero); put_raw(sB, 1, own ? s_raw : zero); }
+    if (t < L.ti_cnt) put_raw(sB, 2 + t, load_vec_rw(&vwy[(size_t)L.n + L.ti_lo + t]).from_mont());
+  }
+  if (!(which & 2)) return;
   if (t == 0) {
-    Fr zero = Fr::zero();
-    bool own = L.singles != 0;
     Fr rs = (r_raw.to_mont() * s_raw.to_mont()).from_mont();
     put_raw(sA, 0, own ? raw_one() : zero); put_raw(sA, 1, zero); put_raw(sA, 2, own ? r_raw : zero);
-    put_raw(sB, 0, own ? raw_one() : zero); put_raw(sB, 1, own ? s_raw : zero);
     put_raw(sC, 0, own ? s_raw : zero); put_raw(sC, 1, own ? r_raw : zero); put_raw(sC, 2, own ? rs : zero);
   }
   if (t < L.ti_cnt) {
     uint32_t i = L.ti_lo + t;
     Fr v = load_vec_rw(&vwy[i]), w = load_vec_rw(&vwy[(size_t)L.n + i]);
     put_raw(sA, 3 + t, v.from_mont());
-    put_raw(sB, 2 + t, w.from_mont());
     Fr c = s_raw.to_mont() * v + r_raw.to_mont() * w;
     put_raw(sC, 3 + t, c.from_mont());
   }
@@ -189,6 +196,7 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
   k->g2.alloc(nparts);
   k->d_out.alloc(ZK_GROTH16_PROOF_OUT);
   ZK_CUDA(cudaEventCreateWithFlags(&k->ready, cudaEventDisableTiming));
+  ZK_CUDA(cudaEventCreateWithFlags(&k->ready_h, cudaEventDisableTiming));
   ZK_CUDA(cudaEventCreate(&k->t_begin));
   ZK_CUDA(cudaEventCreate(&k->t_end));
   for (cudaEvent_t& e : k->mark) ZK_CUDA(cudaEventCreate(&e));
@@ -196,54 +204,89 @@ int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_cou
   ZK_API_END
 }
 
-// vwy, Hq, flag: on the primary device, ready in stream order on st0.
-static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* flag, cudaStream_t st0, uint8_t* proof_out) {
+// vwy (V | W | Y: coefficients or domain values) is ready on the primary device in stream order on
+// st0; `quotient(st0)` enqueues the computation of Hq.  Order of work on every device:
+//   B's scalars -> B sorted and accumulated (G2) -> B's tail on the auxiliary stream, while
+//   the quotient runs (primary device) -> scalars of A and C -> A and C sorted and accumulated as one
+//   list (G1) -> their tail; so the G2 tail hides behind the quotient's transforms instead of
+//   standing at the end of the proof next to the G1 tail.
+static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* flag, cudaStream_t st0, uint8_t* proof_out,
+                           const std::function<void(cudaStream_t)>& quotient) {
   using namespace zk;
   const int np = (int)k->parts.size();
   ZK_CUDA(cudaEventRecord(k->mark[1], st0));
   if (np > 1) ZK_CUDA(cudaEventRecord(k->ready, st0));
+  // the MSMs are queued on their tables; an error before their tails have been enqueued drains the
+  // devices and drops the queues (PipelineScope)
+  std::vector<std::unique_ptr<PipelineScope<G1Traits>>> scopes1;
+  std::vector<std::unique_ptr<PipelineScope<G2Traits>>> scopes2;
+  for (int p = 0; p < np; p++) {
+    Groth16Part& P = *k->parts[p];
+    scopes1.push_back(std::make_unique<PipelineScope<G1Traits>>(P.qC.table, P.ctx, nullptr, 2));
+    scopes2.push_back(std::make_unique<PipelineScope<G2Traits>>(P.qB.table, P.ctx, nullptr, 1));
+  }
+  auto span_of = [](const G16Layout& L) { return std::max(std::max(L.ti_cnt, L.h_cnt), std::max(L.mid_cnt, 1u)); };
+  // Where B goes.  From 2^15 constraints on: B first, so that its G2 tail hides behind the quotient's
+  // transforms (3.3 ms at 2^20 constraints) and the G1 work.  The price is that tail blocks still
+  // resident keep the persistent G1 accumulation from taking its two blocks per SM for a while; at
+  // 2^16 constraints that costs a circuit with well-spread B scalars 0.3 ms and gains the multiply
+  // chain (whose G2 tail carries a heavy-bucket fix-up) 0.9 ms.  Tiny circuits keep B after A and C,
+  // with the two tails side by side at the end.
+  const bool early_b = k->n >= (1u << 15);
+  k->early_b_last = early_b;
+  auto run_b = [&](Groth16Part& P, int p, cudaStream_t st, bool tail_now) {
+    const G16Layout& L = P.lay;
+    k_groth16_scalars<<<cdiv(std::max(L.ti_cnt, 1u), 128), 128, 0, st>>>(L, 1, vwy, Hq, k->d_sol.p, P.mid_index.p, k->d_rs.p,
+                                                                          P.sA.p, P.qB.scalars.p, P.qC.scalars.p);
+    XYZZ<Fp2>* rB = np > 1 ? k->g2.p + p : P.r2.p;
+    uint8_t* o = np > 1 ? nullptr : k->d_out.p;       // one part: wire bytes straight from the tail
+    P.qB.table.run(P.qB.scalars.p, P.qB.table.n, rB, o ? o + ZK_G1_OUT : nullptr, st);                     // B
+    P.qB.table.sort_accumulate(st);
+    if (P.ctx == 0) ZK_CUDA(cudaEventRecord(k->mark[2], st));
+    if (tail_now) {
+      cudaStream_t aux = fork_aux(st);
+      P.qB.table.tail(aux);                           // joined after the G1 tail has been enqueued
+    }
+  };
+  // ---- B on every device (large circuits) ---------------------------------------------------------
+  if (early_b)
+    for (int p = 0; p < np; p++) {
+      Groth16Part& P = *k->parts[p];
+      CtxScope scope(P.ctx);
+      cudaStream_t st = stream_of(P.ctx);
+      if (P.ctx != 0) ZK_CUDA(cudaStreamWaitEvent(st, k->ready, 0));
+      run_b(P, p, st, true);
+    }
+  // ---- h on the primary device -------------------------------------------------------------------
+  quotient(st0);
+  ZK_CUDA(cudaEventRecord(k->mark[3], st0));
+  if (np > 1) ZK_CUDA(cudaEventRecord(k->ready_h, st0));
+  // ---- A and C on every device (then B, for small circuits) -----------------------------------------
   for (int p = 0; p < np; p++) {
     Groth16Part& P = *k->parts[p];
     const G16Layout& L = P.lay;
     CtxScope scope(P.ctx);
     cudaStream_t st = stream_of(P.ctx);
-    if (P.ctx != 0) ZK_CUDA(cudaStreamWaitEvent(st, k->ready, 0));
-    uint32_t span = std::max(std::max(L.ti_cnt, L.h_cnt), std::max(L.mid_cnt, 1u));
-    // the scalars of this part's three MSMs, read from the primary device's V | W, h and witness
-    k_groth16_scalars<<<cdiv(span, 128), 128, 0, st>>>(L, vwy, Hq, k->d_sol.p, P.mid_index.p, k->d_rs.p, P.sA.p,
-                                                        P.qB.scalars.p, P.qC.scalars.p);
     const bool primary = P.ctx == 0;
-    if (primary) ZK_CUDA(cudaEventRecord(k->mark[2], st));
-    // the three MSMs are queued first; an error before their tails have been enqueued drains the
-    // device and drops the queue (PipelineScope)
-    PipelineScope<G1Traits> scope1(P.qC.table, P.ctx, nullptr, 2);
-    PipelineScope<G2Traits> scope2(P.qB.table, P.ctx, nullptr, 1);
+    if (!primary) ZK_CUDA(cudaStreamWaitEvent(st, k->ready_h, 0));
+    k_groth16_scalars<<<cdiv(span_of(L), 128), 128, 0, st>>>(L, 2, vwy, Hq, k->d_sol.p, P.mid_index.p, k->d_rs.p, P.sA.p,
+                                                              P.qB.scalars.p, P.qC.scalars.p);
     XYZZ<Fp>* rA = np > 1 ? k->g1.p + p : P.r1.p;
     XYZZ<Fp>* rC = np > 1 ? k->g1.p + np + p : P.r1.p + 1;
-    XYZZ<Fp2>* rB = np > 1 ? k->g2.p + p : P.r2.p;
-    uint8_t* o = np > 1 ? nullptr : k->d_out.p;       // one part: wire bytes straight from the tail
+    uint8_t* o = np > 1 ? nullptr : k->d_out.p;
     P.qC.table.run(P.sA.p, 3 + L.ti_cnt, rA, o, st);                                                       // A  } queued: one sort and
     P.qC.table.run(P.qC.scalars.p, P.qC.table.n, rC, o ? o + ZK_G1_OUT + ZK_G2_OUT : nullptr, st);         // C  } one accumulation
-    P.qB.table.run(P.qB.scalars.p, P.qB.table.n, rB, o ? o + ZK_G1_OUT : nullptr, st);                     // B
-    // the throughput-bound halves back to back on this stream, then the two latency-bound tails side
-    // by side (G2 on the auxiliary stream)
-    P.qC.table.sort_accumulate(st, primary ? k->mark[3] : nullptr);
-    if (primary) ZK_CUDA(cudaEventRecord(k->mark[4], st));
-    P.qB.table.sort_accumulate(st);
+    P.qC.table.sort_accumulate(st, primary ? k->mark[4] : nullptr);
     if (primary) ZK_CUDA(cudaEventRecord(k->mark[5], st));
-    static const int tail_mode = env_int("ZKB200_TAIL_MODE", 0);   // experiment knob: 1 = both tails on one stream, 2 = G2 only, 3 = G1 only
-    if (tail_mode == 0) {
+    if (early_b) {
+      P.qC.table.tail(st);
+    } else {
+      run_b(P, p, st, false);
       cudaStream_t aux = fork_aux(st);
       P.qB.table.tail(aux, 2);
       P.qC.table.tail(st, 2);
-      join_aux(st);
-    } else {
-      if (tail_mode != 3) P.qB.table.tail(st);
-      if (primary && tail_mode == 1) ZK_CUDA(cudaEventRecord(k->mark[5], st));   // [6] then times the G1 tail alone
-      if (tail_mode != 2) P.qC.table.tail(st);
-      P.qB.table.abort_queue();
-      P.qC.table.abort_queue();
     }
+    join_aux(st);
     if (primary) ZK_CUDA(cudaEventRecord(k->mark[6], st));
     if (np > 1) ZK_CUDA(cudaEventRecord(P.done, st));
   }
@@ -291,8 +334,8 @@ int zk_groth16_prove(uint64_t pk_handle, uint64_t qap_handle, const uint8_t* sol
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaEventRecord(k->mark[0], st));
-  q.eval(k->d_sol.p, st);
-  groth16_finish(k, q.Vc.p, q.H.p, q.flag.p, st, proof_out);
+  q.combine(k->d_sol.p, st);
+  groth16_finish(k, q.Vc.p, q.H.p, q.flag.p, st, proof_out, [&](cudaStream_t s0) { q.quotient_from_work(s0); });
   ZK_API_END
 }
 
@@ -317,8 +360,7 @@ int zk_groth16_prove_coeffs(uint64_t pk_handle, uint64_t qap_handle, const uint8
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaEventRecord(k->mark[0], st));
   q.set_coeffs(qh->d_raw.p, st);
-  q.quotient_from_work(st);
-  groth16_finish(k, q.Vc.p, q.H.p, q.flag.p, st, proof_out);
+  groth16_finish(k, q.Vc.p, q.H.p, q.flag.p, st, proof_out, [&](cudaStream_t s0) { q.quotient_from_work(s0); });
   ZK_API_END
 }
 
@@ -341,8 +383,8 @@ int zk_groth16_prove_r1cs(uint64_t pk_handle, uint64_t domain_handle, const uint
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaEventRecord(k->mark[0], st));
-  d.eval(k->d_sol.p, st);
-  groth16_finish(k, d.evals.p, d.H.p, d.flag.p, st, proof_out);
+  d.values(k->d_sol.p, st);
+  groth16_finish(k, d.evals.p, d.H.p, d.flag.p, st, proof_out, [&](cudaStream_t s0) { d.quotient(s0); });
   ZK_API_END
 }
 
@@ -359,17 +401,24 @@ int zk_groth16_last_device_ms(uint64_t pk_handle, float* ms) {
 }
 
 // Stage split of the last zk_groth16_prove* on this key, in ms (CUDA events on the primary device's
-// stream): [0] witness upload, [1] QAP evaluation + quotient h, [2] MSM scalars, [3] counting sort of
-// A and C (one list), [4] their accumulation (one launch), [5] B sorted + accumulated (the primary
-// device's part), [6] tails of the G1 and G2 MSMs side by side, [7] wait for the other devices +
-// combine + download.
+// stream): [0] witness upload, [1] QAP evaluation (V | W | Y), [2] B: scalars, sort, accumulation,
+// [3] quotient h (B's tail runs beside it on the auxiliary stream), [4] A and C: scalars and counting
+// sort (one list), [5] their accumulation (one launch), [6] G1 tail + what is left of the G2 tail,
+// [7] wait for the other devices + combine + download.
 int zk_groth16_last_stage_ms(uint64_t pk_handle, float out[8]) {
   ZK_API_BEGIN
   using namespace zk;
   auto* k = static_cast<Groth16Key*>(lookup_handle(pk_handle, 4));
   ZK_REQUIRE(out, ZK_EARG, "groth16_last_stage_ms: null argument");
-  cudaEvent_t seq[9] = {k->t_begin, k->mark[0], k->mark[1], k->mark[2], k->mark[3], k->mark[4], k->mark[5], k->mark[6], k->t_end};
-  for (int i = 0; i < 8; i++) ZK_CUDA(cudaEventElapsedTime(&out[i], seq[i], seq[i + 1]));
+  // consecutive marks when B ran first; for small circuits the events fall in the order
+  // begin, 0, 1, 3, 4, 5, 2, 6, end and the same eight quantities are read off pairwise
+  cudaEvent_t* m = k->mark;
+  cudaEvent_t early[8][2] = {{k->t_begin, m[0]}, {m[0], m[1]}, {m[1], m[2]}, {m[2], m[3]}, {m[3], m[4]}, {m[4], m[5]}, {m[5], m[6]}, {m[6], k->t_end}};
+  cudaEvent_t late[8][2] = {{k->t_begin, m[0]}, {m[0], m[1]}, {m[5], m[2]}, {m[1], m[3]}, {m[3], m[4]}, {m[4], m[5]}, {m[2], m[6]}, {m[6], k->t_end}};
+  for (int i = 0; i < 8; i++) {
+    cudaEvent_t* pr = k->early_b_last ? early[i] : late[i];
+    ZK_CUDA(cudaEventElapsedTime(&out[i], pr[0], pr[1]));
+  }
   ZK_API_END
 }
 

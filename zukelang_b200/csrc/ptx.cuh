@@ -17,6 +17,7 @@
 #define ZK_D inline
 #define ZK_NI inline
 #define ZK_UNROLL
+#define ZK_NOUNROLL
 namespace ptx {
 static thread_local uint32_t cc_ = 0;
 inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; cc_ = (uint32_t)(t >> 32); return (uint32_t)t; }
@@ -39,6 +40,7 @@ inline uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { return mul_lo(a, b
 #define ZK_D __device__
 #define ZK_NI __device__ __noinline__
 #define ZK_UNROLL _Pragma("unroll")
+#define ZK_NOUNROLL _Pragma("unroll 1")
 namespace ptx {
 ZK_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 ZK_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
