@@ -60,6 +60,7 @@ void BaseTable<T>::load(const uint8_t* host_raw, const uint8_t* host_inf, uint32
   cfg = choose_config(n, precompute, force_c);
   size_t nwin = precompute ? cfg.W : 1;
   ZK_REQUIRE((uint64_t)nwin * n < (1ull << 31), ZK_EARG, "table too large for 31-bit point indices");
+  ZK_REQUIRE((uint64_t)n * cfg.W < (1ull << 32), ZK_EARG, "table too large for 32-bit entry positions");
   pts.alloc(nwin * n);
   skip.alloc(n);
   DevBuf<uint8_t> d_raw((size_t)n * T::RAW);
@@ -171,7 +172,7 @@ void BaseTable<T>::ensure_queue(int slots) {
   const int most = (int)std::max<uint64_t>(1, (1ull << 29) / per_msm);
   slots = std::max(1, std::min(std::min(slots, most), MSM_QUEUE));
   if (slots <= queue_cap) return;
-  ZK_REQUIRE(queued == 0, ZK_EARG, "cannot resize the queue while MSMs are queued");
+  ZK_REQUIRE(queued == 0 && pending == 0, ZK_EARG, "cannot resize the queue while MSMs are queued");
   const uint32_t nb = cfg.nbuckets();
   const size_t nbq = (size_t)slots * nb;
   const uint32_t cpw = cfg.B / cfg.L;
@@ -193,7 +194,7 @@ template <class T>
 void BaseTable<T>::set_pipelined(bool on, int depth) {
   if (on) {
     if (depth <= 0) depth = env_int("ZKB200_QUEUE", MSM_QUEUE);
-    if (queued == 0) ensure_queue(depth);   // cannot grow under queued MSMs: the current capacity stays
+    if (queued == 0 && pending == 0) ensure_queue(depth);   // cannot grow under queued MSMs: the current capacity stays
     queue_limit = std::max(std::max(1, queued), std::min(depth, queue_cap));
   }
   pipelined = on;

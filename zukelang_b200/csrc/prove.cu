@@ -222,6 +222,7 @@ static void groth16_finish(zk::Groth16Key* k, const Fr* vwy, const Fr* Hq, int* 
   std::vector<std::unique_ptr<PipelineScope<G2Traits>>> scopes2;
   for (int p = 0; p < np; p++) {
     Groth16Part& P = *k->parts[p];
+    CtxScope scope(P.ctx);                            // the first use sizes the queue: on the part's own device
     scopes1.push_back(std::make_unique<PipelineScope<G1Traits>>(P.qC.table, P.ctx, nullptr, 2));
     scopes2.push_back(std::make_unique<PipelineScope<G2Traits>>(P.qB.table, P.ctx, nullptr, 1));
   }
