@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 MAC32_PER_POINT = 48_000          # 16 windows x 3 000 MAC32 (G1 XYZZ mixed add)
 LOG_N = 20
-NCU_DRAM_BYTES_PER_LAUNCH = 3_046_744_160   # k_accumulate, 2^20 points, c = 17 (profiles/r01_ncu_accumulate.md)
+NCU_DRAM_BYTES_PER_MSM = 3_052_184_568      # k_accumulate, one 2^20-point MSM, c = 17 (profiles/r02_ncu_accumulate.md)
 SEED_SCALARS, SEED_BASES = 0x5A554B45, 0x42415345
 
 
@@ -526,7 +526,7 @@ def run_gpu_arm(args):
                        "parallelism": "base-range shards x%d, all_gather of 96-B partial sums (one per group of %d steps)" % (world, QUEUE if pipelined else 1), "setup_s": setup_s, "host_affinity": affinity},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "Mpts/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 144,
-                    "api": "zk_g1_table_msm_batch: K host scalar vectors (pinned) in, K points out, uploads double-buffered",
+                    "api": "zk_g1_table_msm_batch: K host scalar vectors (pinned) in, K points out; a group of vectors is uploaded while the previous group is accumulated",
                     "h2d_gbs_measured": h2d_gbs, "h2d_bound_mpts": h2d_gbs * 1e9 / 32 / 1e6 * world,
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "timing": "K-step call repeated %d times after one warm-up call, median reported; wall clock, max over ranks" % E2E_REPS,
@@ -535,8 +535,8 @@ def run_gpu_arm(args):
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "int32-imad", "kernel": "k_accumulate<Fp>", "achieved": achieved,
                          "peak": peak_mac32 / 1e12, "unit": "TMAC32/s", "frac": achieved / (peak_mac32 / 1e12),
-                         "traffic": (NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and args.logn == 20 and c == 17) else None),
-                         "traffic_source": "profiles/r01_ncu_accumulate.md (ncu --set full, dram__bytes_read+write per 2^20-point MSM)",
+                         "traffic": (NCU_DRAM_BYTES_PER_MSM if (world == 1 and args.logn == 20 and c == 17) else None),
+                         "traffic_source": "profiles/r02_ncu_accumulate.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of a one-MSM launch; algorithmic: 15 x 96 B + 32 B per point = 1.54 GB)",
                          "kernel_ms": acc_avg, "kernel_ms_note": "k_accumulate launch durations summed over the timed region (CUDA events on the launching stream) / MSMs processed; one launch accumulates all the MSMs of a join",
                          "launches_in_timed_region": timed_joins, "msms_per_launch": timed_msms / max(timed_joins, 1),
                          "timed_region_stage_ms_per_step": [x / timed_msms for x in timed_stage_ms],
@@ -551,12 +551,12 @@ def run_gpu_arm(args):
         line.update({k: v for k, v in legs.items()})
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            sample = 1 << 15
+            sample = min(1 << 19, n_total)     # ~10 s of the reference's algorithm on 16 cores
             sc_raw = host0.numpy().tobytes()[:sample * 32]
             secs, out = cpu_fold_msm(bases[:sample * 96].tobytes(), sc_raw, sample, threads)
             line["cpu_baseline"] = {"value": sample / secs / 1e6, "unit": "Mpts/s", "cores": threads, "kind": "port",
-                                    "sample": "first 2^15 of the 2^20 points, oracle/c fold of double-and-add scalar muls "
-                                              "(curve.ml:91-118) on all host threads, %.1f s" % secs}
+                                    "sample": "first 2^%d of the 2^%d points, oracle/c fold of double-and-add scalar muls "
+                                              "(curve.ml:91-118) on all host threads, %.1f s" % (sample.bit_length() - 1, args.logn, secs)}
             try:                                                   # informational; never lose the headline line
                 n_timed = min(1 << 18, n_total)
                 line["cpu_pippenger"] = cpu_pippenger_line(bases[:n_timed * 96].tobytes(),
