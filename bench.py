@@ -151,6 +151,8 @@ def load_c_oracle():
 def cpu_fold_msm(bases_raw, scalars_raw, n, threads):
     """The oracle's restatement of curve.ml:91-118 on `threads` host cores; returns (seconds, out96)."""
     lib = load_c_oracle()
+    if n * 96 > len(bases_raw) or n * 32 > len(scalars_raw):
+        raise ValueError("cpu_fold_msm: %d points asked of buffers holding %d" % (n, len(bases_raw) // 96))
     out = (ctypes.c_uint8 * 96)()
     t0 = time.perf_counter()
     lib.zkoracle_g1_msm_fold(bases_raw, scalars_raw, n, threads, out)
@@ -172,6 +174,8 @@ def cpu_pippenger_msm(bases_raw, scalars_raw, n, threads, c=16):
 def cpu_pippenger_line(bases_raw, scalars_raw, n_check, fold_out, n_timed, threads):
     """The informational ``cpu_pippenger`` object of the JSON line: checked against the fold on the
     cpu_baseline sample, timed on a larger prefix of the same workload."""
+    if max(n_check, n_timed) * 96 > len(bases_raw) or max(n_check, n_timed) * 32 > len(scalars_raw):
+        raise ValueError("cpu_pippenger_line: %d / %d points asked of buffers holding %d" % (n_check, n_timed, len(bases_raw) // 96))
     _, chk = cpu_pippenger_msm(bases_raw[:n_check * 96], scalars_raw[:n_check * 32], n_check, threads)
     secs, _ = cpu_pippenger_msm(bases_raw[:n_timed * 96], scalars_raw[:n_timed * 32], n_timed, threads)
     return {"value": n_timed / secs / 1e6, "unit": "Mpts/s", "cores": threads, "window_bits": 16,
@@ -558,7 +562,7 @@ def run_gpu_arm(args):
                                     "sample": "first 2^%d of the 2^%d points, oracle/c fold of double-and-add scalar muls "
                                               "(curve.ml:91-118) on all host threads, %.1f s" % (sample.bit_length() - 1, args.logn, secs)}
             try:                                                   # informational; never lose the headline line
-                n_timed = min(1 << 18, n_total)
+                n_timed = min(max(1 << 18, sample), n_total)      # never shorter than the sample it is checked on
                 line["cpu_pippenger"] = cpu_pippenger_line(bases[:n_timed * 96].tobytes(),
                                                            host0.numpy().tobytes()[:n_timed * 32],
                                                            sample, out, n_timed, threads)

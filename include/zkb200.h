@@ -216,7 +216,11 @@ int zk_groth16_prove_coeffs(uint64_t pk, uint64_t qap, const uint8_t *vwy, const
  * zk_groth16_prove's.
  * zk_eval_domain_load: w = barycentric weights 1 / prod_{i != j} (j - i), t_shift[k] = t(n + k).
  * zk_r1cs_load: CSR matrix `which` (0 = Gate.l, 1 = Gate.r, 2 = Gate.lhs; circuit.ml:75) with n
- * rows and m columns (variables in increasing Var order).  Handles are freed with zk_qap_free. */
+ * rows and m columns (variables in increasing Var order).  Handles are freed with zk_qap_free.
+ * zk_groth16_prove_r1cs: `sol` = m canonical scalars in host memory (pinned memory makes the
+ * upload one asynchronous DMA) — or in the primary device's memory, complete before the call: a
+ * sharded caller (one process per GPU) uploads 1/N of the witness per rank and all-gathers it over
+ * NVLink instead of sending the whole witness down every PCIe link. */
 int zk_eval_domain_load(size_t n, const uint8_t *w, const uint8_t *t_shift, uint64_t *handle);
 int zk_r1cs_load(uint64_t domain, int which, size_t m, const uint32_t *row_ptr, const uint32_t *col,
                  const uint8_t *val);
@@ -241,6 +245,10 @@ typedef struct {
 
 /* Device time (ms, CUDA events on the primary device's stream: first upload to last download) of
  * the last zk_groth16_prove* call on this key; for bench.py. */
+/* One process per GPU: adds the k shards' partial results — k proof-out buffers, as returned by
+ * zk_groth16_prove* on keys loaded with shard_count = k — into the finished proof (one upload, one
+ * launch, one download; replaces three zk_g*_sum calls). */
+int zk_groth16_combine(const uint8_t *parts, size_t k, uint8_t proof_out[ZK_GROTH16_PROOF_OUT]);
 int zk_groth16_last_device_ms(uint64_t pk, float *ms);
 /* Stage split of that time, in ms (primary device): [0] witness upload, [1] QAP evaluation
  * (V | W | Y), [2] B: scalars, counting sort, accumulation, [3] quotient h(x) — B's tail runs beside

@@ -62,6 +62,12 @@ def test_bench_cpu_legs_agree():
     line = bench.cpu_pippenger_line(bases_raw, sc_raw, 64, fold, n, 4)
     assert line["agrees_with_fold"] is True and line["value"] > 0 and line["unit"] == "Mpts/s"
     assert line["cores"] == 4 and "not the reference's algorithm" in line["sample"]
+    # a sample longer than the buffers is refused, not read out of bounds (bench.py hands slices to C)
+    import pytest
+    with pytest.raises(ValueError):
+        bench.cpu_pippenger_line(bases_raw[:32 * 96], sc_raw[:32 * 32], 64, fold, 32, 4)
+    with pytest.raises(ValueError):
+        bench.cpu_fold_msm(bases_raw[:32 * 96], sc_raw[:32 * 32], 64, 4)
 
 
 def test_ocaml_externals_match_the_stubs():

@@ -152,12 +152,20 @@ def run(zk, logn, iters, circuit="mulchain", dist=None, quiet=False):
     h, n_mid = load_key(zk, circ, td, dom.w, (rank, world))
     setup_s = time.time() - t0
     sols = []
+    m = len(circ.variables)
+    per = (m + world - 1) // world                     # scalars of the witness each rank uploads when sharded
     for i in range(2):
         sol = witness(rng.randrange(R))
         # the witness the caller hands to prove lives in PINNED host memory (the upload is then one
         # asynchronous DMA at link speed; from pageable memory the same 32 MB take ~3 ms at 2^20)
-        pinned = torch.frombuffer(bytearray(fr_vector(sol[k] for k in circ.variables)), dtype=torch.uint8).pin_memory()
+        raw = bytearray(fr_vector(sol[k] for k in circ.variables)) + bytearray(32 * (per * world - m))
+        pinned = torch.frombuffer(raw, dtype=torch.uint8).pin_memory()
         sols.append((sol, pinned))
+    if dist:
+        # one process per GPU: every rank uploads ITS 1/N of the witness and the ranks all-gather it on
+        # the devices (NVLink) instead of pushing the whole witness down all N PCIe links at once
+        d_part = torch.empty(32 * per, dtype=torch.uint8, device="cuda")
+        d_full = torch.empty(32 * per * world, dtype=torch.uint8, device="cuda")
     out = (ctypes.c_uint8 * _lib.GROTH16_PROOF_OUT)()
     wall, dev, ok = [], [], True
     stages = []
@@ -172,7 +180,14 @@ def run(zk, logn, iters, circuit="mulchain", dist=None, quiet=False):
             dist.barrier()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        _lib.check(zk.zk_groth16_prove_r1cs(h, dom.handle, sol_b.data_ptr(), r.to_bytes(32, "little"), s.to_bytes(32, "little"), out))
+        if dist:
+            d_part.copy_(sol_b[32 * per * rank:32 * per * (rank + 1)], non_blocking=True)
+            dist.all_gather_into_tensor(d_full, d_part)
+            torch.cuda.current_stream().synchronize()      # the library runs on its own stream
+            sol_ptr = d_full.data_ptr()
+        else:
+            sol_ptr = sol_b.data_ptr()
+        _lib.check(zk.zk_groth16_prove_r1cs(h, dom.handle, sol_ptr, r.to_bytes(32, "little"), s.to_bytes(32, "little"), out))
         proof = bytes(out)
         if dist:
             proof = D.combine_groth16(D.all_gather_bytes(proof))
@@ -201,9 +216,10 @@ def run(zk, logn, iters, circuit="mulchain", dist=None, quiet=False):
            "stages_ms": dict(zip(("upload", "qap_values", "B_g2_scalars_sort_accumulate", "quotient_h", "AC_g1_scalars_sort", "AC_g1_accumulate", "tails", "combine_download"),
                                  stages[len(stages) // 2])),
            "stages_note": "CUDA events on this process' primary stream, one timed proof (rank 0's when sharded)",
-           "setup_s": setup_s, "witness_memory": "pinned host", "h2d_bytes_per_proof": 32 * len(circ.variables) + 64, "d2h_bytes_per_proof": 576,
+           "setup_s": setup_s, "witness_memory": "pinned host" + ("; each rank uploads 1/%d of it, all_gather on the devices" % world if dist else ""),
+           "h2d_bytes_per_proof": 32 * (per if dist else m) + 64, "d2h_bytes_per_proof": 576,
            "timing": "wall clock around the C-ABI prove call%s, median of %d (max over ranks); device_ms = CUDA events inside "
-                     "the call, first upload to last download" % (" + all_gather of the 576-B partials + zk_g*_sum" if dist else "", iters),
+                     "the call, first upload to last download" % (" (and, before it, this rank's 1/N witness upload + the witness all_gather) + all_gather of the 576-B partials + zk_g*_sum" if dist else "", iters),
            "msm_points": {"A_g1": n + 3, "C_g1": 3 + 2 * n + n_mid, "B_g2": n + 2}}
     if not quiet and rank == 0:
         print(json.dumps(rec), flush=True)

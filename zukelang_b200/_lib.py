@@ -73,6 +73,7 @@ SIGNATURES = {
     "zk_groth16_pk_load": (c_int, [c_void_p, c_int, c_int, POINTER(c_uint64)]),
     "zk_groth16_prove": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zk_groth16_prove_coeffs": (c_int, [c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zk_groth16_combine": (c_int, [c_void_p, c_size_t, c_void_p]),
     "zk_groth16_last_device_ms": (c_int, [c_uint64, POINTER(ctypes.c_float)]),
     "zk_groth16_last_stage_ms": (c_int, [c_uint64, POINTER(ctypes.c_float)]),
     "zk_eval_domain_load": (c_int, [c_size_t, c_void_p, c_void_p, POINTER(c_uint64)]),

@@ -137,9 +137,55 @@ k_groth16_scalars(G16Layout L, int which, const Fr* __restrict__ vwy, const Fr* 
   }
 }
 
+// Sum of the shards' partial proof elements (one process per GPU: every rank returns the partial
+// a | b | c of its base ranges): block 0 adds the k partial a, block 1 the b, block 2 the c, each
+// from the uncompressed bytes at the head of its proof-out slot, and writes the finished
+// uncompressed | compressed bytes.  A partial that does not parse raises err.
+template <class T>
+__device__ void sum_wire_points(const uint8_t* first, size_t stride, uint32_t k, uint8_t* out, int* err) {
+  XYZZ<typename T::F> acc = XYZZ<typename T::F>::inf();
+  for (uint32_t r = 0; r < k; r++) {
+    Affine<typename T::F> p;
+    if (T::parse(first + (size_t)r * stride, p)) { atomicExch(err, 1); continue; }
+    acc.add(XYZZ<typename T::F>::from_affine(p));      // the compact out-of-line addition: one thread, a short chain
+  }
+  Affine<typename T::F> a = acc.to_affine();
+  T::serialize(a, out);
+}
+static __global__ void k_groth16_combine(const uint8_t* __restrict__ parts, uint32_t k, uint8_t* __restrict__ out, int* err) {
+  if (threadIdx.x) return;
+  if (blockIdx.x == 0) sum_wire_points<G1Traits>(parts, ZK_GROTH16_PROOF_OUT, k, out, err);
+  else if (blockIdx.x == 1) sum_wire_points<G2Traits>(parts + ZK_G1_OUT, ZK_GROTH16_PROOF_OUT, k, out + ZK_G1_OUT, err);
+  else sum_wire_points<G1Traits>(parts + ZK_G1_OUT + ZK_G2_OUT, ZK_GROTH16_PROOF_OUT, k, out + ZK_G1_OUT + ZK_G2_OUT, err);
+}
+
 }  // namespace zk
 
 extern "C" {
+
+// parts: k proof-out buffers (ZK_GROTH16_PROOF_OUT bytes each) returned by zk_groth16_prove* on keys
+// loaded with shard_count = k; proof_out: the finished proof.  One upload, one launch, one download.
+int zk_groth16_combine(const uint8_t* parts, size_t k, uint8_t* proof_out) {
+  ZK_API_BEGIN
+  using namespace zk;
+  ZK_REQUIRE(parts && proof_out && k > 0 && k <= 4096, ZK_EARG, "groth16_combine: bad arguments");
+  cudaStream_t st = default_stream();
+  static thread_local DevBuf<uint8_t> d_in, d_out;     // calls are serialised (ApiGuard) and stream-ordered
+  static thread_local DevBuf<int> d_err;
+  d_in.ensure(k * ZK_GROTH16_PROOF_OUT);
+  d_out.ensure(ZK_GROTH16_PROOF_OUT);
+  d_err.ensure(1);
+  ZK_CUDA(cudaMemcpyAsync(d_in.p, parts, k * ZK_GROTH16_PROOF_OUT, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+  k_groth16_combine<<<3, 32, 0, st>>>(d_in.p, (uint32_t)k, d_out.p, d_err.p);
+  ZK_CUDA(cudaGetLastError());
+  int err = 0;
+  ZK_CUDA(cudaMemcpyAsync(proof_out, d_out.p, ZK_GROTH16_PROOF_OUT, cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ZK_CUDA(cudaStreamSynchronize(st));
+  ZK_REQUIRE(err == 0, ZK_EPOINT, "groth16_combine: partial point not canonical or not on the curve");
+  ZK_API_END
+}
 
 int zk_groth16_pk_load(const zk_groth16_pkey* pk, int shard_index, int shard_count, uint64_t* handle) {
   ZK_API_BEGIN
@@ -380,7 +426,9 @@ int zk_groth16_prove_r1cs(uint64_t pk_handle, uint64_t domain_handle, const uint
   check_rs(r, s);
   cudaStream_t st = default_stream();
   ZK_CUDA(cudaEventRecord(k->t_begin, st));
-  ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyHostToDevice, st));
+  // `sol` may also be a device pointer (a witness all-gathered over NVLink by a sharded caller): the
+  // copy infers its direction; a device buffer must be complete before the call
+  ZK_CUDA(cudaMemcpyAsync(k->d_sol.p, sol, (size_t)k->m * 32, cudaMemcpyDefault, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p, r, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(k->d_rs.p + 8, s, 32, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaEventRecord(k->mark[0], st));

@@ -74,7 +74,13 @@ _G16 = ((0, G1_RAW, False), (_lib.G1_OUT, G2_RAW, True), (_lib.G1_OUT + _lib.G2_
 def combine_groth16(partials: Sequence[bytes], engine=None) -> bytes:
     """Add the shards' partial (a, b, c) — zk_groth16_prove outputs with shard_count > 1 — into the
     proof-out buffer of the whole proof."""
-    engine = engine or CudaEngine()
+    if engine is None:                                    # the library adds all three elements in one call
+        buf = b"".join(partials)
+        if len(buf) != len(partials) * _lib.GROTH16_PROOF_OUT:
+            raise ValueError("combine_groth16: every partial is a %d-byte proof-out buffer" % _lib.GROTH16_PROOF_OUT)
+        res = (ctypes.c_uint8 * _lib.GROTH16_PROOF_OUT)()
+        _lib.check(_lib.lib().zk_groth16_combine(buf, len(partials), res))
+        return bytes(res)
     out = b""
     for off, raw, is_g2 in _G16:
         pts = b"".join(p[off:off + raw] for p in partials)
