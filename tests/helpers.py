@@ -1,6 +1,5 @@
 """Shared helpers for the parity tests: oracle <-> C-ABI byte conversions."""
 import ctypes
-import random
 
 from oracle import bls12_381 as O
 

@@ -16,7 +16,6 @@ import pytest
 
 from oracle import bls12_381 as O
 from oracle import zk as Z
-from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 R = O.R
