@@ -236,6 +236,24 @@ def run_reference_arm(args):
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
+def tail_tree_levels(c, bucket_windows, q_join, sm_count):
+    """Launches of k_reduce_tree in one batched tail: the chunk width L of the bucket reduction as
+    csrc/msm_impl.cuh:tail() picks it (the narrowest of 4..32 that keeps the chunk threads of the
+    q_join queued MSMs within one warp per scheduler), then 64-wide trees down to one element."""
+    buckets = 1 << (c - 1)
+    L = 4
+    while L < 32 and q_join * buckets * bucket_windows // L > sm_count * 4 * 32:
+        L <<= 1
+    L = min(L, buckets)
+    levels, cnt = 0, buckets // L
+    while True:
+        levels += 1
+        cnt = (cnt + 63) // 64
+        if cnt <= 1:
+            break
+    return levels
+
+
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
@@ -497,13 +515,8 @@ def run_gpu_arm(args):
         # combine+finalize) + the shard sum for N > 1
         group = QUEUE if pipelined else 1
         groups = max(timed_joins, (args.steps + group - 1) // group)     # a table beyond 2^21 points joins more often
-        cpw = (1 << (c - 1)) // (16 if (pipelined and min(group, args.steps) >= 3) else 4)
-        levels, cnt = 0, cpw
-        while True:
-            levels += 1
-            cnt = (cnt + 63) // 64
-            if cnt == 1:
-                break
+        levels = tail_tree_levels(c, int(info[2]), min(group, args.steps),
+                                  torch.cuda.get_device_properties(local_rank).multi_processor_count)
         gpu_launches = groups * (5 + 4 + levels + (1 if world > 1 else 0))
         assert timed_msms == args.steps or timed_joins == 64, (timed_joins, groups, timed_msms)   # the ring keeps 64 joins
         acc_avg = timed_stage_ms[1] / timed_msms                 # k_accumulate time per MSM inside the timed region

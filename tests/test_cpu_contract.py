@@ -86,3 +86,16 @@ def test_ocaml_externals_match_the_stubs():
         assert needle in ml, needle
     # no load/free per proof any more ("missing" 4)
     assert "key_free hk" not in ml and "qap_free hq" not in ml
+
+
+def test_bench_launch_count_helper():
+    """bench.py's gpu_launches claim mirrors the tail's chunk-width rule (csrc/msm_impl.cuh:tail)."""
+    import bench
+    # 2^20 points, c = 17, 20 MSMs per join on 148 SMs: L = 32 -> 2048 chunks -> 32 -> 1
+    assert bench.tail_tree_levels(17, 1, 20, 148) == 2
+    # the 8-GPU shard: c = 16, L = 32 -> 1024 chunks -> 16 -> 1
+    assert bench.tail_tree_levels(16, 1, 20, 148) == 2
+    # a single MSM: L = 4 -> 16384 chunks -> 256 -> 4 -> 1
+    assert bench.tail_tree_levels(17, 1, 1, 148) == 3
+    # tiny window: never below one level
+    assert bench.tail_tree_levels(4, 1, 1, 148) == 1
